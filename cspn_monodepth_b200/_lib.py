@@ -1,0 +1,79 @@
+"""ctypes binding of ``lib/libcspn_b200.so`` (C ABI declared in ``include/cspn_b200.h``).
+
+There is deliberately no fallback: if the CUDA library is missing and cannot be built,
+importing the operators raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+from . import build as _build
+
+_c_int, _c_i64, _c_sz, _c_vp = ctypes.c_int, ctypes.c_int64, ctypes.c_size_t, ctypes.c_void_p
+
+# name -> (restype, argtypes); mirrors include/cspn_b200.h one to one (checked by tests/test_abi.py)
+SIGNATURES = {
+    "cspn_abi_version": (_c_int, []),
+    "cspn_error_string": (ctypes.c_char_p, [_c_int]),
+    "cspn_set_path": (_c_int, [_c_int]),
+    "cspn_last_path": (_c_int, []),
+    "cspn_last_launch_count": (_c_int, []),
+    "cspn_fwd_workspace_bytes": (_c_sz, [_c_int] * 7),
+    "cspn_bwd_workspace_bytes": (_c_sz, [_c_int] * 7),
+    "cspn_fwd_f32": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_int, _c_vp] + [_c_int] * 7 + [_c_vp, _c_sz, _c_vp]),
+    "cspn_fwd_f16": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_int, _c_vp] + [_c_int] * 7 + [_c_vp, _c_sz, _c_vp]),
+    "cspn_bwd_f32": (_c_int, [_c_vp, _c_vp, _c_i64, _c_int, _c_vp, _c_vp, _c_int, _c_vp, _c_vp] + [_c_int] * 7 + [_c_vp, _c_sz, _c_vp]),
+    "cspn_bwd_f16": (_c_int, [_c_vp, _c_vp, _c_i64, _c_int, _c_vp, _c_vp, _c_int, _c_vp, _c_vp] + [_c_int] * 7 + [_c_vp, _c_sz, _c_vp]),
+    "cspn_fwd_host_f32": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_int, _c_vp] + [_c_int] * 7 + [_c_vp]),
+    "cspn_fwd_host_f16": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_int, _c_vp] + [_c_int] * 7 + [_c_vp]),
+}
+
+PATH_AUTO, PATH_GENERIC, PATH_FUSED = 0, 1, 2
+MODE_NEW, MODE_OURS = 0, 1
+
+_lock = threading.Lock()
+_lib = None
+
+
+class CspnError(RuntimeError):
+    """Raised for a non-zero return code of the C ABI (RuntimeError like the reference's ATen errors)."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"{message} (code {code})")
+        self.code = code
+
+
+def library_path() -> str:
+    return _build.SO
+
+
+def load() -> ctypes.CDLL:
+    """Load (building first if the sources are newer and nvcc exists) the C-ABI library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        so = _build.SO
+        try:
+            if _build.needs_build():
+                _build.build()
+        except Exception as exc:  # no nvcc on this machine: fall through to the prebuilt file if there is one
+            if not os.path.exists(so):
+                raise RuntimeError(
+                    "libcspn_b200.so is missing and could not be built - the CSPN operators have no fallback. "
+                    f"Run `python -m cspn_monodepth_b200.build` on a machine with nvcc. Cause: {exc}") from exc
+        lib = ctypes.CDLL(so)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError = ABI mismatch, fail loudly
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def check(code: int) -> None:
+    if code != 0:
+        raise CspnError(code, load().cspn_error_string(code).decode())

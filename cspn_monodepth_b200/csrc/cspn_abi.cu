@@ -1,0 +1,230 @@
+// C ABI of the CSPN B200 library (include/cspn_b200.h): argument validation, path selection
+// and the host-buffer convenience entry points.  No torch types anywhere in this library.
+#include <atomic>
+#include <cstring>
+
+#include "cspn_common.cuh"
+
+namespace cspn {
+
+CallStats& call_stats()
+{
+    static thread_local CallStats s = {0, 0};
+    return s;
+}
+
+namespace {
+
+std::atomic<int> g_path{CSPN_PATH_AUTO};
+
+int validate_common(const void* guidance, int64_t gbs, const void* depth, const void* sparse, int sparse_channels,
+                    int B, int C, int H, int W, int iters, int ksize, int mode, TapTable* tt)
+{
+    if (mode != CSPN_MODE_NEW && mode != CSPN_MODE_OURS) return CSPN_ERR_BAD_MODE;
+    if (!make_taps(mode, ksize, tt)) return CSPN_ERR_BAD_KERNEL_SIZE;
+    if (B < 0 || C < 1 || H < 1 || W < 1 || iters < 0) return CSPN_ERR_BAD_SHAPE;
+    if ((uint64_t)B * (uint64_t)C * (uint64_t)H * (uint64_t)W > (1ull << 40)) return CSPN_ERR_BAD_SHAPE;
+    if (B == 0) return CSPN_OK;
+    if (!guidance || !depth) return CSPN_ERR_NULL_POINTER;
+    if (gbs < (int64_t)tt->n * H * W) return CSPN_ERR_BAD_STRIDE;
+    if (sparse && sparse_channels != 1 && sparse_channels != C) return CSPN_ERR_BAD_SPARSE_CHANNELS;
+    return CSPN_OK;
+}
+
+bool overlaps(const void* a, size_t an, const void* b, size_t bn)
+{
+    const char* pa = (const char*)a; const char* pb = (const char*)b;
+    return a && b && pa < pb + bn && pb < pa + an;
+}
+
+bool use_fused(int C, int H, int W, int iters, int ksize, int mode, int* err)
+{
+    const int path = g_path.load(std::memory_order_relaxed);
+    const bool ok = fused_supported(C, H, W, iters, ksize, mode);
+    if (path == CSPN_PATH_FUSED && !ok && err) *err = CSPN_ERR_BAD_KERNEL_SIZE;
+    return path != CSPN_PATH_GENERIC && ok;
+}
+
+template <typename T>
+int forward_impl(const T* guidance, int64_t gbs, const T* depth, const T* sparse, int sparse_channels, T* out,
+                 int B, int C, int H, int W, int iters, int ksize, int mode, void* ws, size_t ws_bytes, void* stream)
+{
+    TapTable tt;
+    int rc = validate_common(guidance, gbs, depth, sparse, sparse_channels, B, C, H, W, iters, ksize, mode, &tt);
+    if (rc != CSPN_OK || B == 0) return rc;
+    if (!out) return CSPN_ERR_NULL_POINTER;
+    const size_t hw = (size_t)H * W, nout = (size_t)B * C * hw * sizeof(T);
+    if (overlaps(out, nout, depth, nout) || overlaps(out, nout, guidance, (size_t)B * gbs * sizeof(T)) ||
+        (sparse && overlaps(out, nout, sparse, (size_t)B * sparse_channels * hw * sizeof(T))))
+        return CSPN_ERR_ALIAS;
+    FwdArgs<T> a{guidance, gbs, depth, sparse, sparse ? sparse_channels : 1, out, B, C, H, W, iters, ksize, mode, ws, ws_bytes, (cudaStream_t)stream};
+    call_stats().launches = 0;
+    int err = CSPN_OK;
+    if (iters > 0 && use_fused(C, H, W, iters, ksize, mode, &err)) {
+        rc = fused_forward<T>(a);
+        if (rc == CSPN_OK) call_stats().path = CSPN_PATH_FUSED;
+        return rc;
+    }
+    if (err != CSPN_OK) return err;
+    if (iters > 0) {
+        const size_t need = generic_fwd_workspace(B, C, H, W, tt.n);
+        if (!ws || ws_bytes < need) return CSPN_ERR_WORKSPACE;
+    }
+    rc = generic_forward<T>(a, tt);
+    if (rc == CSPN_OK) call_stats().path = CSPN_PATH_GENERIC;
+    return rc;
+}
+
+template <typename T>
+int backward_impl(const T* grad_out, const T* guidance, int64_t gbs, int Cg, const T* depth, const T* sparse,
+                  int sparse_channels, T* grad_guidance, T* grad_depth, int B, int C, int H, int W, int iters,
+                  int ksize, int mode, void* ws, size_t ws_bytes, void* stream)
+{
+    TapTable tt;
+    int rc = validate_common(guidance, gbs, depth, sparse, sparse_channels, B, C, H, W, iters, ksize, mode, &tt);
+    if (rc != CSPN_OK || B == 0) return rc;
+    if (!grad_out || !grad_guidance || !grad_depth) return CSPN_ERR_NULL_POINTER;
+    if (Cg < tt.n) return CSPN_ERR_BAD_STRIDE;
+    if (iters > 0) {
+        const size_t need = generic_bwd_workspace(B, C, H, W, iters, tt.n);
+        if (!ws || ws_bytes < need) return CSPN_ERR_WORKSPACE;
+    }
+    BwdArgs<T> a{grad_out, guidance, gbs, Cg, depth, sparse, sparse ? sparse_channels : 1, grad_guidance, grad_depth,
+                 B, C, H, W, iters, ksize, mode, ws, ws_bytes, (cudaStream_t)stream};
+    call_stats().launches = 0;
+    rc = generic_backward<T>(a, tt);
+    if (rc == CSPN_OK) call_stats().path = CSPN_PATH_GENERIC;
+    return rc;
+}
+
+// H2D -> forward -> D2H with stream-ordered scratch; returns once `out` holds the result.
+template <typename T>
+int forward_host_impl(const T* guidance, int64_t gbs, const T* depth, const T* sparse, int sparse_channels, T* out,
+                      int B, int C, int H, int W, int iters, int ksize, int mode, void* stream_)
+{
+    TapTable tt;
+    int rc = validate_common(guidance, gbs, depth, sparse, sparse_channels, B, C, H, W, iters, ksize, mode, &tt);
+    if (rc != CSPN_OK || B == 0) return rc;
+    if (!out) return CSPN_ERR_NULL_POINTER;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const size_t hw = (size_t)H * W;
+    // Only the K*K-1 channels that are read travel over PCIe; the device copy is packed (batch stride taps*H*W).
+    const size_t g_bytes = (size_t)B * tt.n * hw * sizeof(T), d_bytes = (size_t)B * C * hw * sizeof(T);
+    const size_t s_bytes = sparse ? (size_t)B * sparse_channels * hw * sizeof(T) : 0;
+    const size_t ws_bytes = cspn_fwd_workspace_bytes(B, C, H, W, iters, ksize, mode);
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t total = up(g_bytes) + 2 * up(d_bytes) + up(s_bytes) + up(ws_bytes);
+    char* base = nullptr;
+    cudaError_t e = cudaMallocAsync((void**)&base, total, stream);
+    if (e != cudaSuccess) return (int)e;
+    char* p = base;
+    T* dg = (T*)p; p += up(g_bytes);
+    T* dd = (T*)p; p += up(d_bytes);
+    T* dout = (T*)p; p += up(d_bytes);
+    T* ds = sparse ? (T*)p : nullptr; p += up(s_bytes);
+    void* dws = ws_bytes ? (void*)p : nullptr;
+    if (gbs == (int64_t)tt.n * (int64_t)hw) e = cudaMemcpyAsync(dg, guidance, g_bytes, cudaMemcpyHostToDevice, stream);
+    else e = cudaMemcpy2DAsync(dg, tt.n * hw * sizeof(T), guidance, (size_t)gbs * sizeof(T), tt.n * hw * sizeof(T), B, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dd, depth, d_bytes, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess && sparse) e = cudaMemcpyAsync(ds, sparse, s_bytes, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) {
+        rc = forward_impl<T>(dg, (int64_t)tt.n * (int64_t)hw, dd, ds, sparse_channels, dout, B, C, H, W, iters, ksize, mode, dws, ws_bytes, stream);
+        if (rc == CSPN_OK) e = cudaMemcpyAsync(out, dout, d_bytes, cudaMemcpyDeviceToHost, stream);
+    }
+    cudaError_t e2 = cudaFreeAsync(base, stream);
+    cudaError_t e3 = cudaStreamSynchronize(stream);
+    if (rc != CSPN_OK) return rc;
+    if (e != cudaSuccess) return (int)e;
+    if (e2 != cudaSuccess) return (int)e2;
+    return (int)e3;
+}
+
+}  // namespace
+}  // namespace cspn
+
+using namespace cspn;
+
+extern "C" {
+
+int cspn_abi_version(void) { return CSPN_B200_ABI_VERSION; }
+
+const char* cspn_error_string(int code)
+{
+    switch (code) {
+        case CSPN_OK: return "success";
+        case CSPN_ERR_NULL_POINTER: return "cspn: required pointer is NULL";
+        case CSPN_ERR_BAD_SHAPE: return "cspn: bad shape (need B >= 0, C,H,W >= 1, iters >= 0)";
+        case CSPN_ERR_BAD_KERNEL_SIZE: return "cspn: unsupported kernel size for this mode/path (mode NEW needs 3; mode OURS needs odd 3..7)";
+        case CSPN_ERR_BAD_MODE: return "cspn: unknown mode";
+        case CSPN_ERR_BAD_STRIDE: return "cspn: guidance has fewer than K*K-1 channels (batch stride / Cg too small)";
+        case CSPN_ERR_WORKSPACE: return "cspn: workspace missing or smaller than cspn_*_workspace_bytes()";
+        case CSPN_ERR_BAD_SPARSE_CHANNELS: return "cspn: sparse must have 1 or C channels";
+        case CSPN_ERR_ALIAS: return "cspn: out aliases an input";
+        default: break;
+    }
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "cspn: unknown error";
+}
+
+int cspn_set_path(int path)
+{
+    if (path < CSPN_PATH_AUTO || path > CSPN_PATH_FUSED) return g_path.load();
+    return g_path.exchange(path);
+}
+int cspn_last_path(void) { return call_stats().path; }
+int cspn_last_launch_count(void) { return call_stats().launches; }
+
+size_t cspn_fwd_workspace_bytes(int B, int C, int H, int W, int iters, int ksize, int mode)
+{
+    TapTable tt;
+    if (!make_taps(mode, ksize, &tt) || B < 1 || C < 1 || H < 1 || W < 1 || iters < 1) return 0;
+    if (use_fused(C, H, W, iters, ksize, mode, nullptr)) return 0;
+    return generic_fwd_workspace(B, C, H, W, tt.n);
+}
+
+size_t cspn_bwd_workspace_bytes(int B, int C, int H, int W, int iters, int ksize, int mode)
+{
+    TapTable tt;
+    if (!make_taps(mode, ksize, &tt) || B < 1 || C < 1 || H < 1 || W < 1 || iters < 1) return 0;
+    return generic_bwd_workspace(B, C, H, W, iters, tt.n);
+}
+
+int cspn_fwd_f32(const float* guidance, int64_t gbs, const float* depth, const float* sparse, int sparse_channels,
+                 float* out, int B, int C, int H, int W, int iters, int ksize, int mode, void* ws, size_t ws_bytes, void* stream)
+{
+    return forward_impl<float>(guidance, gbs, depth, sparse, sparse_channels, out, B, C, H, W, iters, ksize, mode, ws, ws_bytes, stream);
+}
+int cspn_fwd_f16(const void* guidance, int64_t gbs, const void* depth, const void* sparse, int sparse_channels,
+                 void* out, int B, int C, int H, int W, int iters, int ksize, int mode, void* ws, size_t ws_bytes, void* stream)
+{
+    return forward_impl<__half>((const __half*)guidance, gbs, (const __half*)depth, (const __half*)sparse, sparse_channels,
+                                (__half*)out, B, C, H, W, iters, ksize, mode, ws, ws_bytes, stream);
+}
+int cspn_bwd_f32(const float* grad_out, const float* guidance, int64_t gbs, int Cg, const float* depth, const float* sparse,
+                 int sparse_channels, float* grad_guidance, float* grad_depth, int B, int C, int H, int W, int iters,
+                 int ksize, int mode, void* ws, size_t ws_bytes, void* stream)
+{
+    return backward_impl<float>(grad_out, guidance, gbs, Cg, depth, sparse, sparse_channels, grad_guidance, grad_depth,
+                                B, C, H, W, iters, ksize, mode, ws, ws_bytes, stream);
+}
+int cspn_bwd_f16(const void* grad_out, const void* guidance, int64_t gbs, int Cg, const void* depth, const void* sparse,
+                 int sparse_channels, void* grad_guidance, void* grad_depth, int B, int C, int H, int W, int iters,
+                 int ksize, int mode, void* ws, size_t ws_bytes, void* stream)
+{
+    return backward_impl<__half>((const __half*)grad_out, (const __half*)guidance, gbs, Cg, (const __half*)depth,
+                                 (const __half*)sparse, sparse_channels, (__half*)grad_guidance, (__half*)grad_depth,
+                                 B, C, H, W, iters, ksize, mode, ws, ws_bytes, stream);
+}
+int cspn_fwd_host_f32(const float* guidance, int64_t gbs, const float* depth, const float* sparse, int sparse_channels,
+                      float* out, int B, int C, int H, int W, int iters, int ksize, int mode, void* stream)
+{
+    return forward_host_impl<float>(guidance, gbs, depth, sparse, sparse_channels, out, B, C, H, W, iters, ksize, mode, stream);
+}
+int cspn_fwd_host_f16(const void* guidance, int64_t gbs, const void* depth, const void* sparse, int sparse_channels,
+                      void* out, int B, int C, int H, int W, int iters, int ksize, int mode, void* stream)
+{
+    return forward_host_impl<__half>((const __half*)guidance, gbs, (const __half*)depth, (const __half*)sparse, sparse_channels,
+                                     (__half*)out, B, C, H, W, iters, ksize, mode, stream);
+}
+
+}  // extern "C"

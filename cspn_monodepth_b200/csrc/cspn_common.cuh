@@ -1,0 +1,87 @@
+// Shared declarations of the CSPN B200 library (internal; the public ABI is include/cspn_b200.h).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/cspn_b200.h"
+
+namespace cspn {
+
+constexpr int kMaxTaps = 48;  // 7x7 - 1
+
+// Tap k reads depth at p + (dy[k], dx[k]).  Mode NEW: table of CSPN_new.py:43-67 (+ crop :87);
+// mode OURS: row-major K*K taps without the centre (CSPN_ours.py:37-41, pac.py:89).
+struct TapTable {
+    int n;
+    int8_t dy[kMaxTaps];
+    int8_t dx[kMaxTaps];
+};
+
+inline bool make_taps(int mode, int ksize, TapTable* t)
+{
+    if (mode == CSPN_MODE_NEW) {
+        if (ksize != 3) return false;
+        const int8_t ady[8] = {+1, +1, +1, 0, 0, -1, -1, -1};
+        const int8_t adx[8] = {+1, 0, -1, +1, -1, +1, 0, -1};
+        t->n = 8;
+        for (int k = 0; k < 8; ++k) { t->dy[k] = ady[k]; t->dx[k] = adx[k]; }
+        return true;
+    }
+    if (mode != CSPN_MODE_OURS || ksize < 3 || ksize > 7 || (ksize & 1) == 0) return false;
+    const int p = ksize / 2;
+    int n = 0;
+    for (int iy = 0; iy < ksize; ++iy)
+        for (int ix = 0; ix < ksize; ++ix) {
+            if (iy == p && ix == p) continue;
+            t->dy[n] = (int8_t)(iy - p);
+            t->dx[n] = (int8_t)(ix - p);
+            ++n;
+        }
+    t->n = n;
+    return true;
+}
+
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+
+__device__ __forceinline__ float signf(float v) { return (float)((v > 0.f) - (v < 0.f)); }
+
+// Problem description shared by all launchers.
+template <typename T>
+struct FwdArgs {
+    const T* guidance; int64_t gbs;
+    const T* depth; const T* sparse; int sparse_channels;
+    T* out;
+    int B, C, H, W, iters, ksize, mode;
+    void* ws; size_t ws_bytes;
+    cudaStream_t stream;
+};
+template <typename T>
+struct BwdArgs {
+    const T* grad_out; const T* guidance; int64_t gbs; int Cg;
+    const T* depth; const T* sparse; int sparse_channels;
+    T* grad_guidance; T* grad_depth;
+    int B, C, H, W, iters, ksize, mode;
+    void* ws; size_t ws_bytes;
+    cudaStream_t stream;
+};
+
+// Per-host-thread bookkeeping reported through cspn_last_path / cspn_last_launch_count.
+struct CallStats { int path; int launches; };
+CallStats& call_stats();
+
+// generic path (cspn_generic.cu): one launch per iteration, any tap table
+size_t generic_fwd_workspace(int B, int C, int H, int W, int taps);
+size_t generic_bwd_workspace(int B, int C, int H, int W, int iters, int taps);
+template <typename T> int generic_forward(const FwdArgs<T>& a, const TapTable& tt);
+template <typename T> int generic_backward(const BwdArgs<T>& a, const TapTable& tt);
+
+// fused path (cspn_fused3x3.cu): whole recurrence in one launch, 3x3 only
+bool fused_supported(int C, int H, int W, int iters, int ksize, int mode);
+template <typename T> int fused_forward(const FwdArgs<T>& a);
+
+}  // namespace cspn

@@ -1,0 +1,37 @@
+"""Ways to put the B200 modules into the reference's networks without editing them.
+
+* :func:`install` registers this package's modules under the reference's module names
+  (``network.libs.post_process.CSPN_new`` / ``CSPN_ours``) so that
+  ``from network.libs.post_process.CSPN_new import AffinityPropagate`` (``unet_cspn_nyu.py:9``) and
+  ``from network.libs.post_process.CSPN_ours import AffinityPropagate`` (``unet_ours.py:16``) pick them up.
+  Call it before importing the UNet files.
+* :func:`patch_model` swaps ``model.post_process_layer`` on an already-built reference model
+  (``unet_cspn_nyu.py:357-358`` / ``unet_ours.py:304-305``).  The module has no parameters or buffers,
+  so checkpoints are unaffected.
+"""
+import sys
+
+from . import cspn_new, cspn_ours
+
+
+def install():
+    sys.modules["network.libs.post_process.CSPN_new"] = cspn_new
+    sys.modules["network.libs.post_process.CSPN_ours"] = cspn_ours
+    pkg = sys.modules.get("network.libs.post_process")
+    if pkg is not None:
+        pkg.CSPN_new, pkg.CSPN_ours = cspn_new, cspn_ours
+
+
+def patch_model(model):
+    """Replace every reference ``AffinityPropagate`` inside ``model`` by the B200 one. Returns the count."""
+    n = 0
+    for parent in model.modules():
+        for name, child in list(parent.named_children()):
+            if type(child).__name__ != "AffinityPropagate" or isinstance(child, (cspn_new.AffinityPropagate, cspn_ours.AffinityPropagate)):
+                continue
+            if hasattr(child, "times"):        # CSPN_ours.py:20-22
+                setattr(parent, name, cspn_ours.AffinityPropagate(child.times))
+            else:                              # CSPN_new.py:19-24
+                setattr(parent, name, cspn_new.AffinityPropagate(child.prop_time, child.prop_kernel))
+            n += 1
+    return n

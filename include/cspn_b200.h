@@ -1,0 +1,130 @@
+/* cspn_b200.h - C ABI of the B200-native CSPN affinity-propagation library.
+ *
+ * This is the drop-in boundary for ONE hot path of dontLoveBugs/CSPN_monodepth: the
+ * AffinityPropagate module.  The reference has no native interface for this path (it is
+ * ~20 ATen calls per iteration issued from Python); the entry points below are what a
+ * binding of that module's forward/backward needs, one call per nn.Module.forward /
+ * autograd backward.  Reference interfaces replaced (paths relative to the reference):
+ *
+ *   cspn_fwd_*  mode CSPN_MODE_NEW   network/libs/post_process/CSPN_new.py:26-92
+ *               AffinityPropagate(prop_time, prop_kernel=3).forward(guidance, blur_depth, sparse_depth)
+ *               called from network/unet_cspn_nyu.py:386
+ *   cspn_fwd_*  mode CSPN_MODE_OURS  network/libs/post_process/CSPN_ours.py:24-54
+ *               AffinityPropagate(prop_time).forward(x, guided, sparse_depth)
+ *               (pixel-adaptive conv network/libs/base/pac.py:124-144, Conv2dFn.forward :75-94)
+ *               called from network/unet_ours.py:333
+ *   cspn_bwd_*  autograd through the loops at CSPN_new.py:80-90 / CSPN_ours.py:47-53
+ *               (Conv2dFn.backward, pac.py:96-121)
+ *
+ * Conventions
+ *   - All tensors are NCHW, innermost dimension contiguous, plane stride H*W, channel
+ *     stride H*W.  `guidance` may carry more channels than the K*K-1 taps that are read
+ *     (the NYU UNet hands over 12, unet_cspn_nyu.py:332): it is addressed through
+ *     `guidance_batch_stride` (in ELEMENTS).  Depth has C >= 1 channels that share the
+ *     affinity of their image.  `sparse` may be NULL (no re-injection), or have 1 channel
+ *     (broadcast over C) or C channels (`sparse_channels`).
+ *   - *_f32: every tensor is float.  *_f16: guidance/depth/sparse/out/grads are IEEE half
+ *     (2 bytes), arithmetic is fp32 inside the kernels, the workspace is fp32.
+ *   - Device entry points take DEVICE pointers, enqueue on `stream` (a cudaStream_t passed
+ *     as void*; NULL = legacy default stream), never synchronise, never allocate: scratch
+ *     comes from the caller (`workspace`, size from cspn_*_workspace_bytes).  They are
+ *     stateless, re-entrant, usable from several host threads on different devices (the
+ *     reference's DataParallel replicas, network/libs/base/encoding.py:102-105) and
+ *     capturable in CUDA graphs.  Inputs are never modified; `out` must not alias inputs.
+ *   - Host entry points (cspn_fwd_host_*) take HOST pointers (pinned or pageable), do
+ *     H2D copy -> kernels -> D2H copy on `stream` with stream-ordered device allocations
+ *     and return after the result is in `out` (they synchronise the stream).
+ *   - Return value: 0 = success; CSPN_ERR_* (negative) = rejected arguments, nothing was
+ *     launched; positive = a cudaError_t from the CUDA runtime.  cspn_error_string() maps
+ *     all three.  (The reference's only native convention is "int, checked by _check",
+ *     network/libs/inplace_abn/functions.py:13-16.)
+ *   - There is no CPU fallback: without a CUDA device the calls return a cudaError_t.
+ */
+#ifndef CSPN_B200_H
+#define CSPN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSPN_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define CSPN_API __attribute__((visibility("default")))
+#else
+#define CSPN_API
+#endif
+
+/* mode */
+#define CSPN_MODE_NEW 0  /* abs-normalised, weights indexed at the NEIGHBOUR, border renormalisation (CSPN_new.py) */
+#define CSPN_MODE_OURS 1 /* softmax-normalised, weights indexed at the CENTRE, zero padding (CSPN_ours.py + pac.py) */
+
+/* errors */
+#define CSPN_OK 0
+#define CSPN_ERR_NULL_POINTER (-1)
+#define CSPN_ERR_BAD_SHAPE (-2)      /* B,C,H,W < 1 (B == 0 is a no-op success), iters < 0 */
+#define CSPN_ERR_BAD_KERNEL_SIZE (-3)/* mode NEW: ksize != 3 (CSPN_new.py:122 only works for 3); mode OURS: ksize not odd in [3,7] */
+#define CSPN_ERR_BAD_MODE (-4)
+#define CSPN_ERR_BAD_STRIDE (-5)     /* guidance_batch_stride < (K*K-1)*H*W */
+#define CSPN_ERR_WORKSPACE (-6)      /* workspace NULL or too small */
+#define CSPN_ERR_BAD_SPARSE_CHANNELS (-7)
+#define CSPN_ERR_ALIAS (-8)          /* out aliases an input */
+
+/* path selection (cspn_set_path): which CUDA implementation the forward uses */
+#define CSPN_PATH_AUTO 0    /* fused single-launch kernel whenever the configuration is supported */
+#define CSPN_PATH_GENERIC 1 /* one launch per iteration (any K, any shape); for debugging and A/B timing */
+#define CSPN_PATH_FUSED 2   /* fused kernel or CSPN_ERR_BAD_KERNEL_SIZE if unsupported */
+
+CSPN_API int cspn_abi_version(void);
+CSPN_API const char* cspn_error_string(int code);
+
+/* Process-wide override of the forward path, mainly for tests and benchmarks. Returns the previous value. */
+CSPN_API int cspn_set_path(int path);
+/* Which path the last successful cspn_fwd_* call on this host thread took (CSPN_PATH_GENERIC or CSPN_PATH_FUSED). */
+CSPN_API int cspn_last_path(void);
+/* Number of kernel launches enqueued by the last successful call on this host thread. */
+CSPN_API int cspn_last_launch_count(void);
+
+/* Scratch sizes in bytes (0 is possible). */
+CSPN_API size_t cspn_fwd_workspace_bytes(int B, int C, int H, int W, int iters, int ksize, int mode);
+CSPN_API size_t cspn_bwd_workspace_bytes(int B, int C, int H, int W, int iters, int ksize, int mode);
+
+/* Forward: out[B,C,H,W] = r^iters. iters == 0 copies depth to out. */
+CSPN_API int cspn_fwd_f32(const float* guidance, int64_t guidance_batch_stride,
+                 const float* depth, const float* sparse, int sparse_channels, float* out,
+                 int B, int C, int H, int W, int iters, int ksize, int mode,
+                 void* workspace, size_t workspace_bytes, void* stream);
+CSPN_API int cspn_fwd_f16(const void* guidance, int64_t guidance_batch_stride,
+                 const void* depth, const void* sparse, int sparse_channels, void* out,
+                 int B, int C, int H, int W, int iters, int ksize, int mode,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward: given grad_out[B,C,H,W] writes grad_guidance[B,Cg,H,W] completely (channels that
+ * the forward does not read get exact zeros; batch stride Cg*H*W) and grad_depth[B,C,H,W].
+ * There is no gradient for `sparse` (sign() has zero derivative, CSPN_new.py:78). */
+CSPN_API int cspn_bwd_f32(const float* grad_out, const float* guidance, int64_t guidance_batch_stride, int Cg,
+                 const float* depth, const float* sparse, int sparse_channels,
+                 float* grad_guidance, float* grad_depth,
+                 int B, int C, int H, int W, int iters, int ksize, int mode,
+                 void* workspace, size_t workspace_bytes, void* stream);
+CSPN_API int cspn_bwd_f16(const void* grad_out, const void* guidance, int64_t guidance_batch_stride, int Cg,
+                 const void* depth, const void* sparse, int sparse_channels,
+                 void* grad_guidance, void* grad_depth,
+                 int B, int C, int H, int W, int iters, int ksize, int mode,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* Host-buffer forward (end-to-end path: H2D, kernels, D2H inside the call). */
+CSPN_API int cspn_fwd_host_f32(const float* guidance, int64_t guidance_batch_stride,
+                      const float* depth, const float* sparse, int sparse_channels, float* out,
+                      int B, int C, int H, int W, int iters, int ksize, int mode, void* stream);
+CSPN_API int cspn_fwd_host_f16(const void* guidance, int64_t guidance_batch_stride,
+                      const void* depth, const void* sparse, int sparse_channels, void* out,
+                      int B, int C, int H, int W, int iters, int ksize, int mode, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSPN_B200_H */

@@ -1,0 +1,77 @@
+"""The C-ABI library loads and exports exactly what include/cspn_b200.h declares.  No GPU needed:
+argument validation happens before any CUDA call."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from cspn_monodepth_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "cspn_b200.h")).read()
+    return sorted(set(re.findall(r"CSPN_API\s+[\w\s\*]+?\b(cspn_\w+)\s*\(", text)))
+
+
+def test_header_declares_expected_entry_points():
+    names = _declared()
+    for must in ("cspn_fwd_f32", "cspn_fwd_f16", "cspn_bwd_f32", "cspn_bwd_f16", "cspn_fwd_host_f32",
+                 "cspn_fwd_workspace_bytes", "cspn_bwd_workspace_bytes", "cspn_error_string", "cspn_abi_version"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(_lib.library_path()) if os.path.exists(_lib.library_path()) else _lib.load()
+    for name in _declared():
+        assert hasattr(lib, name), f"{name} declared in cspn_b200.h but not exported"
+
+
+def test_python_binding_covers_header():
+    assert sorted(_lib.SIGNATURES) == _declared()
+
+
+def test_abi_version_and_error_strings():
+    lib = _lib.load()
+    assert lib.cspn_abi_version() == 1
+    assert lib.cspn_error_string(0) == b"success"
+    for code in range(-8, 0):
+        assert lib.cspn_error_string(code).startswith(b"cspn:")
+
+
+def test_argument_validation_without_gpu():
+    lib = _lib.load()
+    one = ctypes.c_float(0.0)
+    p = ctypes.addressof(one)
+
+    def fwd(guidance=p, gbs=8 * 16, depth=p, sparse=None, sc=1, out=p + 0, b=1, c=1, h=4, w=4, iters=2, k=3, mode=0, ws=None, wsb=0):
+        return lib.cspn_fwd_f32(guidance, gbs, depth, sparse, sc, out, b, c, h, w, iters, k, mode, ws, wsb, None)
+
+    assert fwd(mode=7) == -4
+    assert fwd(k=5) == -3                   # CSPN_new only works with prop_kernel 3 (CSPN_new.py:122)
+    assert fwd(k=4, mode=1) == -3
+    assert fwd(h=0) == -2
+    assert fwd(iters=-1) == -2
+    assert fwd(guidance=None) == -1
+    assert fwd(gbs=7 * 16) == -5            # fewer than 8 guidance channels
+    assert fwd(sparse=p, sc=2) == -7
+    assert fwd(b=0) == 0                    # empty batch is a no-op
+    assert fwd(out=p) == -8                 # out aliases depth
+    with pytest.raises(_lib.CspnError):
+        _lib.check(-3)
+
+
+def test_workspace_queries():
+    lib = _lib.load()
+    assert lib.cspn_fwd_workspace_bytes(1, 1, 8, 8, 0, 3, 0) == 0
+    prev = lib.cspn_set_path(_lib.PATH_GENERIC)
+    try:
+        n = lib.cspn_fwd_workspace_bytes(2, 1, 16, 16, 24, 3, 0)
+        assert n >= (2 * 8 + 2 * 2) * 256 * 4
+        assert lib.cspn_fwd_workspace_bytes(2, 1, 16, 16, 12, 5, 1) >= (2 * 24 + 4) * 256 * 4
+    finally:
+        lib.cspn_set_path(prev)
+    assert lib.cspn_bwd_workspace_bytes(1, 1, 16, 16, 24, 3, 0) >= (8 + 8 + 1 + 23 + 3) * 256 * 4
+    assert lib.cspn_bwd_workspace_bytes(1, 1, 16, 16, 24, 4, 0) == 0

@@ -1,0 +1,287 @@
+"""Parity of the CUDA path against the oracle / the reference's golden vectors.  Every call goes through the
+C ABI (ctypes) - either via the drop-in nn.Modules or with raw device pointers.
+
+Tolerances: forward max-abs <= 1e-4 at depth scale 10 (north_star), scaled with the depth range otherwise;
+fp16 I/O: 1 fp16 ulp of the output (2^-10 relative) + the fp32 tolerance; gradients: 1e-4 relative to the
+largest entry.
+"""
+import ctypes
+import threading
+
+import numpy as np
+import pytest
+import torch
+
+import cspn_monodepth_b200 as pkg
+from cspn_monodepth_b200 import _lib, cspn_new, cspn_ours
+from oracle import c_oracle
+from tests.util import assert_close_nan, case_config, make_inputs, nyu_golden_inputs
+
+pytestmark = pytest.mark.gpu
+
+FWD_ATOL = 1e-4
+GRAD_RTOL = 1e-4
+DEV = "cuda:0"
+PATHS = [_lib.PATH_GENERIC, _lib.PATH_AUTO]
+
+
+@pytest.fixture(autouse=True)
+def _need_cuda_and_reset_path():
+    assert torch.cuda.is_available(), "gpu-marked tests need a CUDA device"
+    lib = _lib.load()
+    yield
+    lib.cspn_set_path(_lib.PATH_AUTO)
+
+
+def _cu(a, dtype=torch.float32):
+    return None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(DEV).to(dtype)
+
+
+def _run(mode, g, d, s, iters, requires_grad=False, dtype=torch.float32):
+    tg, td, ts = _cu(g, dtype), _cu(d, dtype), _cu(s, dtype)
+    if requires_grad:
+        tg.requires_grad_(True); td.requires_grad_(True)
+    if mode == 0:
+        y = cspn_new.AffinityPropagate(iters, 3)(tg, td, ts)
+    else:
+        y = cspn_ours.AffinityPropagate(prop_time=iters)(td, tg, sparse_depth=ts)
+    return y, tg, td
+
+
+def _golden_names(golden):
+    return sorted(n for n in golden if "guidance" in golden[n])
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_forward_matches_reference_golden(golden, path):
+    _lib.load().cspn_set_path(path)
+    for name in _golden_names(golden):
+        case = golden[name]
+        mode, _, iters = case_config(name, case)
+        y, _, _ = _run(mode, case["guidance"], case["depth"], case.get("sparse"), iters)
+        scale = max(1.0, float(np.nanmax(np.abs(case["depth"]))) / 10.0)
+        assert_close_nan(y.cpu().numpy(), case["out"], FWD_ATOL * scale, name)
+
+
+def test_backward_matches_reference_autograd(golden):
+    checked = 0
+    for name in _golden_names(golden):
+        case = golden[name]
+        if "grad_out" not in case:
+            continue
+        mode, _, iters = case_config(name, case)
+        y, tg, td = _run(mode, case["guidance"], case["depth"], case.get("sparse"), iters, requires_grad=True)
+        y.backward(_cu(case["grad_out"]))
+        for got, key in ((tg.grad, "grad_guidance"), (td.grad, "grad_depth")):
+            ref = case[key]
+            assert_close_nan(got.cpu().numpy(), ref, GRAD_RTOL * max(1.0, np.abs(ref).max()), f"{name}:{key}")
+        if mode == 0 and case["guidance"].shape[1] > 8:
+            assert torch.count_nonzero(tg.grad[:, 8:]) == 0
+        checked += 1
+    assert checked >= 12
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_nyu_known_answer_and_oracle(golden, path):
+    _lib.load().cspn_set_path(path)
+    g, d, s = nyu_golden_inputs()
+    y, _, _ = _run(0, g, d, s, 24)
+    assert_close_nan(y.cpu().numpy(), golden["A_nyu_seed304228_T24"]["out"], FWD_ATOL, "nyu golden")
+    assert_close_nan(y.cpu().numpy(), c_oracle.forward(g, d, s, 24, 3, 0), FWD_ATOL, "nyu oracle")
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("shape", [(8, 228, 304), (2, 352, 1216), (3, 97, 131), (1, 64, 64), (2, 65, 257), (1, 3, 1000), (1, 500, 5)])
+def test_forward_vs_oracle_shape_grid(path, shape):
+    _lib.load().cspn_set_path(path)
+    b, h, w = shape
+    for mode, cg in ((0, 8), (0, 12), (1, 8)):
+        g, d, s = make_inputs(h * w + mode, b, cg, 1, h, w, density=0.02, neg=(mode == 1))
+        y, _, _ = _run(mode, g, d, s, 24)
+        assert_close_nan(y.cpu().numpy(), c_oracle.forward(g, d, s, 24, 3, mode), FWD_ATOL, f"{shape} mode {mode} cg {cg}")
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("iters", [1, 2, 3, 7, 24, 40])
+def test_iteration_counts(path, iters):
+    _lib.load().cspn_set_path(path)
+    g, d, s = make_inputs(iters, 2, 8, 1, 50, 77, density=0.05)
+    y, _, _ = _run(0, g, d, s, iters)
+    assert_close_nan(y.cpu().numpy(), c_oracle.forward(g, d, s, iters, 3, 0), FWD_ATOL, f"T={iters}")
+    y, _, _ = _run(0, g, d, None, iters)
+    assert_close_nan(y.cpu().numpy(), c_oracle.forward(g, d, None, iters, 3, 0), FWD_ATOL, f"T={iters} no sparse")
+
+
+def test_five_by_five_pac_variant():
+    g, d, s = make_inputs(55, 2, 24, 1, 60, 80, density=0.02)           # cfg4 shape family: K=5, T=12
+    y, _, _ = _run(1, g, d, s, 12)
+    assert_close_nan(y.cpu().numpy(), c_oracle.forward(g, d, s, 12, 5, 1), FWD_ATOL, "5x5")
+    g, d, s = make_inputs(77, 1, 48, 1, 20, 30, density=0.02)
+    y, _, _ = _run(1, g, d, s, 4)
+    assert_close_nan(y.cpu().numpy(), c_oracle.forward(g, d, s, 4, 7, 1), FWD_ATOL, "7x7")
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_multichannel_depth_and_per_channel_sparse(path):
+    _lib.load().cspn_set_path(path)
+    g, d, s = make_inputs(21, 2, 8, 3, 30, 41, density=0.05, sparse_channels=3)
+    y, _, _ = _run(0, g, d, s, 9)
+    assert_close_nan(y.cpu().numpy(), c_oracle.forward(g, d, s, 9, 3, 0), FWD_ATOL, "C=3, sparse C=3")
+    y, _, _ = _run(0, g, d, s[:, :1], 9)
+    assert_close_nan(y.cpu().numpy(), c_oracle.forward(g, d, s[:, :1], 9, 3, 0), FWD_ATOL, "C=3, sparse C=1")
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_fp16_io(path):
+    _lib.load().cspn_set_path(path)
+    g, d, s = make_inputs(16, 2, 8, 1, 120, 200, density=0.05)
+    g16, d16, s16 = (a.astype(np.float16) for a in (g, d, s))
+    y, _, _ = _run(0, g16, d16, s16, 24, dtype=torch.float16)
+    ref = c_oracle.forward(g16.astype(np.float32), d16.astype(np.float32), s16.astype(np.float32), 24, 3, 0)
+    err = np.abs(y.float().cpu().numpy() - ref)
+    assert (err <= np.abs(ref) * 2.0 ** -10 + FWD_ATOL).all(), f"fp16 I/O: max err {err.max():.3e}"
+
+
+def test_fp16_backward_runs_and_is_close():
+    g, d, s = make_inputs(17, 1, 8, 1, 40, 56, density=0.05)
+    g16, d16, s16 = (a.astype(np.float16) for a in (g, d, s))
+    go = np.random.default_rng(3).standard_normal(d.shape).astype(np.float16)
+    y, tg, td = _run(0, g16, d16, s16, 12, requires_grad=True, dtype=torch.float16)
+    y.backward(_cu(go, torch.float16))
+    gg, gd = c_oracle.backward(g16.astype(np.float32), d16.astype(np.float32), s16.astype(np.float32), go.astype(np.float32), 12, 3, 0)
+    assert np.abs(td.grad.float().cpu().numpy() - gd).max() <= 2e-3 * max(1.0, np.abs(gd).max())
+    assert np.abs(tg.grad.float().cpu().numpy() - gg).max() <= 2e-3 * max(1.0, np.abs(gg).max())
+
+
+def test_backward_vs_oracle_larger():
+    for mode, cg, k, iters in ((0, 12, 3, 24), (1, 8, 3, 24), (1, 24, 5, 12)):
+        g, d, s = make_inputs(90 + mode + k, 2, cg, 1, 45, 61, density=0.03)
+        go = np.random.default_rng(5).standard_normal(d.shape).astype(np.float32)
+        y, tg, td = _run(mode, g, d, s, iters, requires_grad=True)
+        y.backward(_cu(go))
+        gg, gd = c_oracle.backward(g, d, s, go, iters, k, mode)
+        assert_close_nan(td.grad.cpu().numpy(), gd, GRAD_RTOL * max(1.0, np.abs(gd).max()), f"gd mode {mode} k {k}")
+        assert_close_nan(tg.grad.cpu().numpy(), gg, GRAD_RTOL * max(1.0, np.abs(gg).max()), f"gg mode {mode} k {k}")
+
+
+# ---- size-independent properties at BASELINE.json's full sizes -------------------------------
+@pytest.mark.parametrize("path", PATHS)
+def test_full_size_properties(path):
+    _lib.load().cspn_set_path(path)
+    for (b, h, w, dtype) in ((8, 228, 304, torch.float32), (4, 352, 1216, torch.float16)):
+        g, d, s = make_inputs(b * h, b, 8, 1, h, w, density=0.01)
+        y, _, _ = _run(0, g, d, s, 24, dtype=dtype)
+        yf = y.float()
+        assert torch.isfinite(yf).all()
+        assert yf.min().item() >= d.min() - 2e-2 and yf.max().item() <= d.max() + 2e-2      # convex combination
+        hit = torch.from_numpy(s > 0).to(DEV)
+        assert torch.equal(y[hit], _cu(d, dtype)[hit])                                        # blur depth re-injected exactly
+        # batch-slice independence, bit exact: the multi-GPU sharding property
+        y0, _, _ = _run(0, g[1:3], d[1:3], s[1:3], 24, dtype=dtype)
+        assert torch.equal(y0, y[1:3])
+        # constant depth is a fixed point; guidance scale invariance
+        const = np.full_like(d, 2.5)
+        yc, _, _ = _run(0, g, const, s, 24, dtype=dtype)
+        assert (yc.float() - 2.5).abs().max().item() < 1e-3
+        y2, _, _ = _run(0, g * np.float32(-2.0), d, s, 24, dtype=dtype)
+        assert (y2.float() - yf).abs().max().item() < (1e-4 if dtype == torch.float32 else 2e-2)
+
+
+def test_extra_and_strided_guidance_channels():
+    g, d, s = make_inputs(31, 2, 12, 1, 33, 47, density=0.05)
+    y12, _, _ = _run(0, g, d, s, 24)
+    y8, _, _ = _run(0, g[:, :8], d, s, 24)
+    assert torch.equal(y12, y8)
+    wide = _cu(g)
+    view = wide.narrow(1, 0, 8)                     # batch stride 12*H*W, no copy
+    y = cspn_new.AffinityPropagate(24, 3)(view, _cu(d), _cu(s))
+    assert torch.equal(y, y8)
+    nc = _cu(d).permute(0, 1, 3, 2).contiguous().permute(0, 1, 3, 2)   # non-contiguous depth gets copied
+    assert torch.equal(cspn_new.AffinityPropagate(24, 3)(view, nc, _cu(s)), y8)
+
+
+def test_inputs_not_modified_and_output_fresh():
+    g, d, s = make_inputs(41, 1, 8, 1, 20, 20, density=0.1)
+    tg, td, ts = _cu(g), _cu(d), _cu(s)
+    y = cspn_new.AffinityPropagate(5, 3)(tg, td, ts)
+    assert torch.equal(tg, _cu(g)) and torch.equal(td, _cu(d)) and torch.equal(ts, _cu(s))
+    assert y.data_ptr() != td.data_ptr()
+
+
+def test_raw_c_abi_pointers_and_errors():
+    lib = _lib.load()
+    g, d, s = make_inputs(51, 1, 8, 1, 24, 40, density=0.05)
+    tg, td, ts = _cu(g), _cu(d), _cu(s)
+    out = torch.empty_like(td)
+    n = lib.cspn_fwd_workspace_bytes(1, 1, 24, 40, 24, 3, 0)
+    ws = torch.empty(max(n, 1), dtype=torch.uint8, device=DEV)
+    stream = torch.cuda.current_stream().cuda_stream
+    rc = lib.cspn_fwd_f32(tg.data_ptr(), 8 * 24 * 40, td.data_ptr(), ts.data_ptr(), 1, out.data_ptr(), 1, 1, 24, 40, 24, 3, 0, ws.data_ptr(), n, stream)
+    assert rc == 0 and lib.cspn_last_launch_count() >= 1
+    torch.cuda.synchronize()
+    assert_close_nan(out.cpu().numpy(), c_oracle.forward(g, d, s, 24, 3, 0), FWD_ATOL, "raw abi")
+    lib.cspn_set_path(_lib.PATH_GENERIC)
+    rc = lib.cspn_fwd_f32(tg.data_ptr(), 8 * 24 * 40, td.data_ptr(), ts.data_ptr(), 1, out.data_ptr(), 1, 1, 24, 40, 24, 3, 0, None, 0, stream)
+    assert rc == -6                                  # generic path without workspace
+    with pytest.raises(RuntimeError):
+        cspn_new.AffinityPropagate(2, 3)(tg.double(), td.double())
+    with pytest.raises(RuntimeError):
+        cspn_new.AffinityPropagate(2, 3)(tg[:, :7], td)
+    with pytest.raises(RuntimeError):
+        cspn_new.AffinityPropagate(2, 3)(tg, td[:, :, :-1])
+
+
+def test_host_buffer_entry_point():
+    lib = _lib.load()
+    g, d, s = make_inputs(61, 2, 12, 1, 50, 70, density=0.05)
+    hg, hd, hs = (torch.from_numpy(a).pin_memory() for a in (g, d, s))
+    out = torch.empty_like(hd).pin_memory()
+    rc = lib.cspn_fwd_host_f32(hg.data_ptr(), 12 * 50 * 70, hd.data_ptr(), hs.data_ptr(), 1, out.data_ptr(), 2, 1, 50, 70, 24, 3, 0, None)
+    assert rc == 0
+    assert_close_nan(out.numpy(), c_oracle.forward(g, d, s, 24, 3, 0), FWD_ATOL, "host entry")
+
+
+def test_cuda_graph_capture_and_threads():
+    g, d, s = make_inputs(71, 2, 8, 1, 64, 96, density=0.05)
+    tg, td, ts = _cu(g), _cu(d), _cu(s)
+    mod = cspn_new.AffinityPropagate(24, 3)
+    eager = mod(tg, td, ts)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        mod(tg, td, ts)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(graph, stream=side):
+            captured = mod(tg, td, ts)
+    graph.replay(); torch.cuda.synchronize()
+    assert torch.equal(captured, eager)
+    results = [None] * 4
+
+    def work(i):
+        with torch.cuda.stream(torch.cuda.Stream()):
+            results[i] = mod(tg, td, ts)
+            torch.cuda.current_stream().synchronize()
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    [t.start() for t in threads]; [t.join() for t in threads]
+    assert all(torch.equal(r, eager) for r in results)
+
+
+def test_end_to_end_training_step_through_module():
+    torch.manual_seed(0)
+    head = torch.nn.Conv2d(4, 9, 3, padding=1).to(DEV)                  # stands in for the UNet's two heads
+    x = torch.rand(2, 4, 40, 52, device=DEV)
+    sparse = (torch.rand(2, 1, 40, 52, device=DEV) < 0.05).float() * 3.0
+    target = torch.rand(2, 1, 40, 52, device=DEV) * 10
+    opt = torch.optim.SGD(head.parameters(), lr=1e-3)
+    cspn = cspn_new.AffinityPropagate(24, 3)
+    losses = []
+    for _ in range(3):
+        feat = head(x)
+        pred = cspn(feat[:, :8], feat[:, 8:9].abs() * 5, sparse)
+        loss = (pred - target).abs().mean()
+        opt.zero_grad(); loss.backward(); opt.step()
+        losses.append(loss.item())
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+    assert pkg.MODE_NEW == 0
