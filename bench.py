@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""Benchmark of the CSPN hot path (BASELINE.json metric: CSPN-24 forward Mpixel/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one forward of the hot path over one batch of synthetic input: at N=1 the workload is
+BASELINE.json configs[1] (batch 8, NYU 304x228, 3x3, 24 iterations, fp32, forward only, mode CSPN_new).
+With N>1 (launched by torchrun, one rank per GPU) every rank runs the same per-GPU batch on its own
+batch slice of the global batch (weak scaling, no collective on the CSPN path); the time is the MAX over
+ranks and `value` the whole-job throughput.
+
+Timing: CUDA events on the launching stream around exactly K steps (torch's current stream is the stream
+the C ABI launches on), barrier + synchronize on both sides; inputs rotate through enough independent
+sets that their footprint exceeds the 126 MB L2, so every step reads its inputs from HBM.
+
+The JSON line also carries:
+  roofline      dominant (only) kernel: algorithmic bytes per launch / measured launch time vs measured HBM peak
+  cpu_baseline  the reference's CPU path (op-for-op PyTorch port, oracle/torch_port.py) on the host cores
+  e2e           the same metric through the host-buffer C-ABI entry point (H2D + kernel + D2H per step)
+  extra         the other BASELINE sizes (KITTI 1216x352 fp16, 5x5 PAC variant) for context
+
+`--impl reference` times the reference's CPU implementation (the port; /root/reference does not exist on
+the GPU box) on the same config and prints the same line with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "CSPN-24 forward Mpixel/s"
+UNIT = "Mpixel/s"
+NYU = dict(B=8, H=228, W=304, iters=24, ksize=3, mode=0, dtype="f32")          # BASELINE.json configs[1]
+KITTI = dict(B=32, H=352, W=1216, iters=24, ksize=3, mode=0, dtype="f16")      # configs[2] (forward part)
+PAC5 = dict(B=16, H=480, W=640, iters=12, ksize=5, mode=1, dtype="f32")        # configs[3]
+L2_BYTES = 126e6
+BYTES_PER_PX = {("f32", 3): 44.0, ("f16", 3): 22.0, ("f32", 5): 108.0, ("f16", 5): 54.0}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-extra", action="store_true", help="skip the context configs (KITTI / 5x5)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    return ap.parse_args()
+
+
+def synth(cfg, seed, pinned=False):
+    """Synthetic inputs of SURVEY.md 8(d): randn guidance, depth in [0,10), NYU sparse density 500/69312."""
+    g = torch.Generator().manual_seed(seed)
+    b, h, w = cfg["B"], cfg["H"], cfg["W"]
+    cg = cfg["ksize"] ** 2 - 1
+    guidance = torch.randn(b, cg, h, w, generator=g)
+    depth = torch.rand(b, 1, h, w, generator=g) * 10.0
+    mask = torch.rand(b, 1, h, w, generator=g) < (500.0 / 69312.0)
+    sparse = mask * (torch.rand(b, 1, h, w, generator=g) * 10.0 + 0.1)
+    dt = torch.float16 if cfg["dtype"] == "f16" else torch.float32
+    out = [t.to(dt).contiguous() for t in (guidance, depth, sparse)]
+    return [t.pin_memory() for t in out] if pinned else out
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz, self._stop = [], set(), None, threading.Event()
+        self.thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.reasons.update(k for k, bit in names.items() if r & bit)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def __enter__(self):
+        if self.nv:
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self.thread:
+            self.thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(workload):
+    """DRAM bytes per launch from the committed ncu --set full capture, if one exists for this workload."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f).get(workload)
+    except Exception:
+        return None
+
+
+def run_module(cfg, sets):
+    from cspn_monodepth_b200 import cspn_new, cspn_ours
+    mod = cspn_new.AffinityPropagate(cfg["iters"], 3) if cfg["mode"] == 0 else cspn_ours.AffinityPropagate(cfg["iters"])
+
+    def step(i):
+        g, d, s = sets[i % len(sets)]
+        return mod(g, d, s) if cfg["mode"] == 0 else mod(d, g, sparse_depth=s)
+    return step
+
+
+def device_sets(cfg, dev, rank):
+    px_bytes = BYTES_PER_PX[(cfg["dtype"], cfg["ksize"])] * cfg["B"] * cfg["H"] * cfg["W"]
+    nsets = max(2, int(np.ceil(1.5 * L2_BYTES / px_bytes)))     # rotating footprint >= 1.5 x L2
+    return [[t.to(dev) for t in synth(cfg, 1000 * rank + i)] for i in range(nsets)], nsets
+
+
+def time_device(cfg, dev, rank, steps, warmup, dist=None, sampler=None):
+    """K timed steps with CUDA events; returns (ms_total_max_over_ranks, launches_per_step, nsets)."""
+    from cspn_monodepth_b200 import _lib
+    lib = _lib.load()
+    sets, nsets = device_sets(cfg, dev, rank)
+    step = run_module(cfg, sets)
+    with torch.no_grad():
+        for i in range(max(3, warmup)):
+            step(i)
+        launches = lib.cspn_last_launch_count()
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ctx = sampler if sampler is not None else _Null()
+        with ctx:
+            e0.record()
+            for i in range(steps):
+                step(i)
+            e1.record()
+            torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms, launches, nsets
+
+
+class _Null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+def time_e2e(cfg, dev, steps):
+    """The same metric through the host-buffer C-ABI call: pinned host inputs, H2D + kernel + D2H every step."""
+    from cspn_monodepth_b200 import _lib
+    lib = _lib.load()
+    fn = lib.cspn_fwd_host_f32 if cfg["dtype"] == "f32" else lib.cspn_fwd_host_f16
+    sets = [synth(cfg, 77 + i, pinned=True) for i in range(2)]
+    outs = [torch.empty_like(s[1]).pin_memory() for s in sets]
+    b, h, w = cfg["B"], cfg["H"], cfg["W"]
+    cg = cfg["ksize"] ** 2 - 1
+    stream = torch.cuda.current_stream(dev).cuda_stream
+
+    def call(i):
+        g, d, s = sets[i % 2]
+        _lib.check(fn(g.data_ptr(), cg * h * w, d.data_ptr(), s.data_ptr(), 1, outs[i % 2].data_ptr(),
+                      b, 1, h, w, cfg["iters"], cfg["ksize"], cfg["mode"], stream))
+    for i in range(3):
+        call(i)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        call(i)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    esz = sets[0][0].element_size()
+    h2d = (cg + 2) * b * h * w * esz
+    d2h = b * h * w * esz
+    return e0.elapsed_time(e1) / steps, h2d, d2h, float(outs[0].float().mean())
+
+
+def cpu_reference(cfg, min_seconds=4.0, max_steps=8, batch=None):
+    """Reference CPU path (op-for-op port) on a bounded sample; returns dict for `cpu_baseline`."""
+    from oracle import torch_port
+    b = batch or cfg["B"]
+    small = dict(cfg, B=b, dtype="f32")                 # the reference is fp32-only (CSPN_new.py:122)
+    g, d, s = synth(small, 5)
+    fwd = (lambda: torch_port.mode_a_forward(g, d, s, cfg["iters"])) if cfg["mode"] == 0 else (lambda: torch_port.mode_b_forward(d, g, s, cfg["iters"]))
+    cores = os.cpu_count() or 1
+    best = None
+    with torch.no_grad():
+        for threads in sorted({1, max(1, cores // 2), cores}):
+            torch.set_num_threads(threads)
+            fwd()
+            t0 = time.perf_counter(); fwd(); dt = time.perf_counter() - t0
+            if best is None or dt < best[1]:
+                best = (threads, dt)
+        torch.set_num_threads(best[0])
+        times = []
+        t_start = time.perf_counter()
+        while len(times) < max_steps and (len(times) < 3 or time.perf_counter() - t_start < min_seconds):
+            t0 = time.perf_counter(); fwd(); times.append(time.perf_counter() - t0)
+    px = b * cfg["H"] * cfg["W"]
+    med = statistics.median(times)
+    return {"value": px / med / 1e6, "unit": UNIT, "cores": best[0], "host_cores": cores, "kind": "port",
+            "sample": f"{len(times)} forwards of batch {b} x {cfg['H']}x{cfg['W']} fp32, {cfg['iters']} iterations, "
+                      f"oracle/torch_port.py (op-for-op PyTorch restatement of CSPN_new.py:26-128), torch {torch.__version__}, "
+                      f"{best[0]} threads (fastest of 1/{max(1, cores // 2)}/{cores})",
+            "ms_per_step": med * 1e3}, times
+
+
+def cpu_c_oracle(cfg):
+    """Stronger CPU baseline for context: the fused C oracle with OpenMP over images."""
+    from oracle import c_oracle
+    g, d, s = (t.numpy() for t in synth(dict(cfg, dtype="f32"), 6))
+    c_oracle.forward(g, d, s, cfg["iters"], cfg["ksize"], cfg["mode"], threads=0)
+    t0 = time.perf_counter(); c_oracle.forward(g, d, s, cfg["iters"], cfg["ksize"], cfg["mode"], threads=0); dt = time.perf_counter() - t0
+    return {"value": cfg["B"] * cfg["H"] * cfg["W"] / dt / 1e6, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            "sample": "1 forward, oracle/cspn_oracle.c (fused C restatement, OpenMP over images)"}
+
+
+def main_reference(args, rank):
+    if rank != 0:
+        return
+    cfg = NYU
+    res, times = cpu_reference(cfg, min_seconds=0.0, max_steps=max(1, args.steps) + max(0, args.warmup))
+    times = times[max(0, min(args.warmup, len(times) - 1)):]
+    ms = statistics.median(times) * 1e3
+    value = cfg["B"] * cfg["H"] * cfg["W"] / (ms * 1e-3) / 1e6
+    res["value"] = value
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(cfg, 1), "cpu_baseline": res,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(cfg, nsets):
+    return {"workload": f"batch {cfg['B']} x {cfg['W']}x{cfg['H']} (NYU shape), 3x3, {cfg['iters']} iterations, fp32, forward only, "
+                        f"mode CSPN_new, per GPU", "per_gpu_batch": cfg["B"], "height": cfg["H"], "width": cfg["W"], "iters": cfg["iters"],
+            "l2_policy": f"inputs rotate over {nsets} independent sets ({nsets} x 24.4 MB > 126 MB L2)", "sharding": "independent batch slices, no collective"}
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        main_reference(args, rank)
+        return
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = NYU
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_total, launches, nsets = time_device(cfg, dev, rank, args.steps, args.warmup, dist, sampler)
+    ms_step = ms_total / args.steps
+    px_step = cfg["B"] * cfg["H"] * cfg["W"]
+    value = world * px_step / (ms_step * 1e-3) / 1e6
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        alg_bytes = BYTES_PER_PX[(cfg["dtype"], cfg["ksize"])] * px_step
+        achieved = alg_bytes / (ms_step * 1e-3) / 1e9
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": workload_config(cfg, nsets), "gpu_launches": launches * args.steps,
+                "clocks": sampler.summary(),
+                "roofline": {"bound": "hbm", "kernel": "cspn::fused3x3_kernel<float,10,8,CSPN_new>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": ncu_traffic("nyu_b8_f32"), "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": alg_bytes, "launch_us": ms_step * 1e3,
+                             "fma_floor_us": px_step * cfg["iters"] * 8 / (148 * 128 * 1.965e9) * 1e6}}
+        e_ms, h2d, d2h, _ = time_e2e(cfg, dev, min(args.steps, 50))
+        line["e2e"] = {"value": px_step / (e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                       "ms_per_step": e_ms, "api": "cspn_fwd_host_f32 (C ABI, pinned host buffers)", "n_gpus": 1}
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"], _ = cpu_reference(cfg)
+            line["cpu_baseline_fused_c"] = cpu_c_oracle(cfg)
+        if world == 1 and not args.no_extra:
+            extra = {}
+            for name, c, st in (("kitti_b32_1216x352_f16_fwd", KITTI, 30), ("pac5x5_b16_640x480_f32_fwd", PAC5, 10)):
+                try:
+                    ms, ln, ns = time_device(c, dev, rank, st, 3)
+                    px = c["B"] * c["H"] * c["W"]
+                    gbs = BYTES_PER_PX[(c["dtype"], c["ksize"])] * px / (ms / st * 1e-3) / 1e9
+                    extra[name] = {"value": px / (ms / st * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms / st, "launches_per_step": ln,
+                                   "roofline_frac": gbs / peak, "input_sets": ns}
+                except Exception as exc:        # context numbers must not take the headline down
+                    extra[name] = {"error": repr(exc)[:200]}
+                torch.cuda.empty_cache()
+            line["extra"] = extra
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

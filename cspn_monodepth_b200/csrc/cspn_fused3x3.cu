@@ -1,8 +1,429 @@
-// placeholder - replaced by the fused kernel
+// Fused CSPN forward for 3x3 neighbourhoods (both reference modes): the whole T-step recurrence in ONE
+// launch.  Replaces the loops at CSPN_new.py:80-90 and CSPN_ours.py:47-53 (pac.py:89-94 per step).
+//
+// Design (B200, sm_100a) - see DESIGN.md section 3 for the derivation and the measured numbers behind it:
+//  * The recurrence is FMA-bound once fused (8 FMA per pixel per step against 44 B of HBM traffic per
+//    pixel in total), and only the register file can feed the FMA pipe: the 8 loop-invariant, pre-
+//    normalised weights of every pixel plus the re-injection term stay in REGISTERS for all T steps
+//    (the reference recomputes the normalisation every step).  A thread owns a 2-wide x P-tall strip of
+//    pixels as packed f32x2 pairs so the inner loop is 8 FFMA2 per pixel pair (fma.rn.f32x2: two FMAs per
+//    issue slot - leaves issue slots for the data movement).
+//  * Left/right neighbours come from warp shuffles, rows above/below from the thread's own registers;
+//    warps of a CTA exchange their edge rows through shared memory once per step.
+//  * A register-resident CTA tile is only 64 x (NW*P) pixels, far smaller than the T-pixel dependency cone,
+//    so CTAs cooperate as a thread-block CLUSTER (up to 16 CTAs, e.g. 5x3 = one whole 304x228 NYU image):
+//    every second step each CTA pushes a 2-pixel-deep halo ring into its neighbours' shared memory over
+//    DSMEM (st.shared::cluster) and the cluster barrier publishes it.  Only at the edge of a cluster tile
+//    that is not an image border does the classic shrinking (trapezoid) halo of T pixels apply.
+//  * HBM traffic is the algorithmic minimum: guidance/depth/sparse are read once (plus halo overlap that
+//    L2 serves), only the final depth is written.
+#include <cooperative_groups.h>
+
 #include "cspn_common.cuh"
+
+namespace cg = cooperative_groups;
+
 namespace cspn {
-bool fused_supported(int, int, int, int, int, int) { return false; }
-template <typename T> int fused_forward(const FwdArgs<T>&) { return CSPN_ERR_BAD_KERNEL_SIZE; }
+namespace {
+
+typedef unsigned long long u64;
+
+constexpr int kTileW = 64;            // 32 lanes x 2 pixels
+constexpr int kHaloX = 2;             // one lane (= one pixel pair) of halo per side between CTAs of a cluster
+constexpr int kHaloY = 2;             // two rows of halo per side between CTAs of a cluster
+constexpr int kPeriod = 2;            // halo refresh period in steps (= halo depth)
+constexpr int kStepX = kTileW - 2 * kHaloX;   // x spacing of CTA tiles inside a cluster (60)
+
+__device__ __forceinline__ u64 pk(float lo, float hi)
+{
+    u64 d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+__device__ __forceinline__ float lo_of(u64 v)
+{
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    return lo;
+}
+__device__ __forceinline__ float hi_of(u64 v)
+{
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    return hi;
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c)
+{
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
+// (x-1,x) and (x+1,x+2) pairs of a row from its (x,x+1) pair: one shuffle + one register move each.
+__device__ __forceinline__ void shifted(u64 a, u64& s1, u64& s2)
+{
+    const float lo = lo_of(a), hi = hi_of(a);
+    const float l = __shfl_up_sync(0xffffffffu, hi, 1), r = __shfl_down_sync(0xffffffffu, lo, 1);
+    s1 = pk(l, lo);
+    s2 = pk(hi, r);
+}
+
+template <typename T>
+struct FusedParams {
+    const T* g; int64_t gbs;
+    const T* depth; const T* sparse; int sparse_channels;
+    T* out;
+    int C, H, W, iters;
+    int cx, cy;           // cluster dims (CTAs)
+    int ntx, nty;         // cluster tiles per image
+    int stepx, stepy;     // origin spacing of cluster tiles
+    int ew, eh;           // extent of one cluster tile
+    int margin;           // decaying halo at cluster-tile edges that are not image borders (= iters)
+};
+
+// Shared memory of one CTA.  rowbuf: per-step edge rows of each warp (intra-CTA, double buffered by step
+// parity).  colbox/rowbox: the halo ring received from cluster neighbours (double buffered by refresh parity).
+template <int NW, int P>
+struct __align__(16) Smem {
+    float rowbuf[2][NW][2][kTileW];
+    float colbox[2][2][NW * P][2];        // [parity][side: 0 left, 1 right][tile row][2 px]
+    float rowbox[2][2][kHaloY][kTileW];   // [parity][side: 0 top, 1 bottom][halo row][tile x]
+};
+
+template <typename T, int P, int NW, int MODE>
+__global__ void __launch_bounds__(NW * 32, 1) fused3x3_kernel(const __grid_constant__ FusedParams<T> p)
+{
+    constexpr int TH = NW * P;
+    constexpr int STEPY = TH - 2 * kHaloY;
+    __shared__ Smem<NW, P> sm;
+
+    cg::cluster_group cluster = cg::this_cluster();
+    const bool multi = p.cx * p.cy > 1;
+    if (multi) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");   // "I am running" (waited before the first push)
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ccx = blockIdx.x % p.cx, ccy = blockIdx.y % p.cy;
+    const int tix = blockIdx.x / p.cx, tiy = blockIdx.y / p.cy;
+    const int plane = blockIdx.z, b = plane / p.C, ch = plane - b * p.C;
+    const bool has_left = ccx > 0, has_right = ccx < p.cx - 1, has_up = ccy > 0, has_down = ccy < p.cy - 1;
+    const int H = p.H, W = p.W;
+    const size_t hw = (size_t)H * W;
+
+    // image coordinates of this thread's strip: columns gx, gx+1, rows gy0 .. gy0+P-1
+    const int gx = tix * p.stepx + ccx * kStepX + 2 * lane;
+    const int gy0 = tiy * p.stepy + ccy * STEPY + warp * P;
+
+    const T* gb = p.g + (size_t)b * p.gbs;
+    const T* db = p.depth + (size_t)plane * hw;
+    const T* sb = p.sparse ? p.sparse + ((size_t)b * p.sparse_channels + (p.sparse_channels == 1 ? 0 : ch)) * hw : nullptr;
+
+    // ---- prologue: loop-invariant weights n'_j = (1-m) * n_j, re-injection c = m*d0, r^0 = d0 -------------
+    // internal tap order j: (dy,dx) row-major without the centre; mode NEW channel k = 7 - j reads the
+    // guidance AT THE NEIGHBOUR p + o (CSPN_new.py:43-67), mode OURS channel j reads it at p (CSPN_ours.py:37-41).
+    // A holds the strip's P rows in P+1 register slots: row i lives in slot i+1 before an even step and in
+    // slot i before an odd one.  Even steps sweep top-down and write new row i into slot i (the slot old row
+    // i-1 just vacated), odd steps sweep bottom-up and write into slot i+1 - no register copies between steps.
+    u64 nw[P][8], cc[P], A[P + 1];
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+        const int gy = gy0 + i;
+        const bool row_in = gy >= 0 && gy < H;
+        const bool in0 = row_in && gx >= 0 && gx < W, in1 = row_in && gx + 1 >= 0 && gx + 1 < W;
+        float w0[8], w1[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int jj = j < 4 ? j : j + 1;
+            const int dy = jj / 3 - 1, dx = jj % 3 - 1;
+            if (MODE == CSPN_MODE_NEW) {
+                const int k = 7 - j, yy = gy + dy, xx = gx + dx;
+                const bool rin = yy >= 0 && yy < H;
+                const T* src = gb + (size_t)k * hw + (size_t)yy * W + xx;
+                w0[j] = (rin && xx >= 0 && xx < W) ? fabsf(to_f32(src[0])) : 0.f;
+                w1[j] = (rin && xx + 1 >= 0 && xx + 1 < W) ? fabsf(to_f32(src[1])) : 0.f;
+            } else {
+                const T* src = gb + (size_t)j * hw + (size_t)gy * W + gx;
+                w0[j] = in0 ? to_f32(src[0]) : 0.f;
+                w1[j] = in1 ? to_f32(src[1]) : 0.f;
+            }
+        }
+        if (MODE == CSPN_MODE_NEW) {
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { s0 += w0[7 - k]; s1 += w1[7 - k]; }     // reference order k = 0..7 (CSPN_new.py:124)
+            const float i0 = __frcp_rn(s0), i1 = __frcp_rn(s1);                   // S = 0 -> inf -> 0*inf = NaN like 0/0
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { w0[j] *= i0; w1[j] *= i1; }
+        } else {
+            float m0 = w0[0], m1 = w1[0];
+#pragma unroll
+            for (int j = 1; j < 8; ++j) { m0 = fmaxf(m0, w0[j]); m1 = fmaxf(m1, w1[j]); }
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { w0[j] = expf(w0[j] - m0); w1[j] = expf(w1[j] - m1); s0 += w0[j]; s1 += w1[j]; }
+            const float i0 = __frcp_rn(s0), i1 = __frcp_rn(s1);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { w0[j] *= i0; w1[j] *= i1; }
+        }
+        float d0 = 0.f, d1 = 0.f, m0 = 0.f, m1 = 0.f;
+        if (in0) { d0 = to_f32(db[(size_t)gy * W + gx]); if (sb) m0 = signf(to_f32(sb[(size_t)gy * W + gx])); }
+        if (in1) { d1 = to_f32(db[(size_t)gy * W + gx + 1]); if (sb) m1 = signf(to_f32(sb[(size_t)gy * W + gx + 1])); }
+        // pixels outside the image are virtual: zero weights, zero value (the reference's zero padding)
+        const float f0 = in0 ? 1.f - m0 : 0.f, f1 = in1 ? 1.f - m1 : 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) nw[i][j] = pk(in0 ? f0 * w0[j] : 0.f, in1 ? f1 * w1[j] : 0.f);
+        cc[i] = pk(m0 * d0, m1 * d1);
+        A[i + 1] = pk(d0, d1);
+    }
+    A[0] = 0ull;
+
+    // which lanes / rows of this CTA tile are authoritative (not halo owned by a cluster neighbour)
+    const int lx0 = has_left ? 1 : 0, lx1 = has_right ? 30 : 31;
+    const int ry0 = has_up ? kHaloY : 0, ry1 = has_down ? TH - 1 - kHaloY : TH - 1;
+    const bool lane_auth = lane >= lx0 && lane <= lx1;
+    const unsigned my_rank = cluster.block_rank();
+
+    if (multi) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+
+    // ---- T propagation steps ---------------------------------------------------------------------------
+    for (int t = 0; t < p.iters; ++t) {
+        // ===== even step: rows in slots 1..P, top-down =====
+        const bool refresh = multi && t > 0;          // t is even here: halo ring (2 deep) is refreshed every 2 steps
+        const int rpar = (t / kPeriod) & 1;
+        if (refresh) {
+            // push the authoritative pixels that lie in a neighbour's halo ring into that neighbour's boxes
+            Smem<NW, P>* left = has_left ? cluster.map_shared_rank(&sm, my_rank - 1) : nullptr;
+            Smem<NW, P>* right = has_right ? cluster.map_shared_rank(&sm, my_rank + 1) : nullptr;
+            if (lane == 1 && has_left) {
+#pragma unroll
+                for (int i = 0; i < P; ++i) {
+                    const int ty = warp * P + i;
+                    if (ty >= ry0 && ty <= ry1) *reinterpret_cast<u64*>(&left->colbox[rpar][1][ty][0]) = A[i + 1];
+                }
+            }
+            if (lane == 30 && has_right) {
+#pragma unroll
+                for (int i = 0; i < P; ++i) {
+                    const int ty = warp * P + i;
+                    if (ty >= ry0 && ty <= ry1) *reinterpret_cast<u64*>(&right->colbox[rpar][0][ty][0]) = A[i + 1];
+                }
+            }
+            if (has_up && warp == 0) {
+                // my tile rows kHaloY .. 2*kHaloY-1 are the upper neighbour's bottom halo rows
+                Smem<NW, P>* up = cluster.map_shared_rank(&sm, my_rank - p.cx);
+                Smem<NW, P>* upl = has_left ? cluster.map_shared_rank(&sm, my_rank - p.cx - 1) : nullptr;
+                Smem<NW, P>* upr = has_right ? cluster.map_shared_rank(&sm, my_rank - p.cx + 1) : nullptr;
+#pragma unroll
+                for (int h = 0; h < kHaloY; ++h) {
+                    const u64 v = A[kHaloY + h + 1];
+                    if (lane_auth) *reinterpret_cast<u64*>(&up->rowbox[rpar][1][h][2 * lane]) = v;
+                    if (lane == 1 && has_left) *reinterpret_cast<u64*>(&upl->colbox[rpar][1][TH - kHaloY + h][0]) = v;
+                    if (lane == 30 && has_right) *reinterpret_cast<u64*>(&upr->colbox[rpar][0][TH - kHaloY + h][0]) = v;
+                }
+            }
+            if (has_down && warp == NW - 1) {
+                Smem<NW, P>* dn = cluster.map_shared_rank(&sm, my_rank + p.cx);
+                Smem<NW, P>* dnl = has_left ? cluster.map_shared_rank(&sm, my_rank + p.cx - 1) : nullptr;
+                Smem<NW, P>* dnr = has_right ? cluster.map_shared_rank(&sm, my_rank + p.cx + 1) : nullptr;
+#pragma unroll
+                for (int h = 0; h < kHaloY; ++h) {
+                    const u64 v = A[P - 2 * kHaloY + h + 1];
+                    if (lane_auth) *reinterpret_cast<u64*>(&dn->rowbox[rpar][0][h][2 * lane]) = v;
+                    if (lane == 1 && has_left) *reinterpret_cast<u64*>(&dnl->colbox[rpar][1][h][0]) = v;
+                    if (lane == 30 && has_right) *reinterpret_cast<u64*>(&dnr->colbox[rpar][0][h][0]) = v;
+                }
+            }
+        }
+        // publish this warp's edge rows for the warps above / below (same CTA)
+        *reinterpret_cast<u64*>(&sm.rowbuf[0][warp][0][2 * lane]) = A[1];
+        *reinterpret_cast<u64*>(&sm.rowbuf[0][warp][1][2 * lane]) = A[P];
+        if (refresh) {
+            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+            asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        } else {
+            __syncthreads();
+        }
+        u64 top = 0ull, bot = 0ull;   // rows -1 and P of this strip (zero above/below the CTA tile)
+        if (warp > 0) top = *reinterpret_cast<const u64*>(&sm.rowbuf[0][warp - 1][1][2 * lane]);
+        if (warp < NW - 1) bot = *reinterpret_cast<const u64*>(&sm.rowbuf[0][warp + 1][0][2 * lane]);
+        if (refresh) {
+            if (has_up && warp == 0) {
+#pragma unroll
+                for (int h = 0; h < kHaloY; ++h) A[h + 1] = *reinterpret_cast<const u64*>(&sm.rowbox[rpar][0][h][2 * lane]);
+            }
+            if (has_down && warp == NW - 1) {
+#pragma unroll
+                for (int h = 0; h < kHaloY; ++h) A[P - kHaloY + h + 1] = *reinterpret_cast<const u64*>(&sm.rowbox[rpar][1][h][2 * lane]);
+            }
+            const bool edge = (lane == 0 && has_left) || (lane == 31 && has_right);
+            if (edge) {
+                const int side = lane == 0 ? 0 : 1;
+                const int ty0 = warp * P;
+#pragma unroll
+                for (int i = 0; i < P; ++i) A[i + 1] = *reinterpret_cast<const u64*>(&sm.colbox[rpar][side][ty0 + i][0]);
+                top = ty0 > 0 ? *reinterpret_cast<const u64*>(&sm.colbox[rpar][side][ty0 - 1][0]) : 0ull;
+                bot = ty0 + P < TH ? *reinterpret_cast<const u64*>(&sm.colbox[rpar][side][ty0 + P][0]) : 0ull;
+            }
+        }
+        // r'(p) = c(p) + sum_j n'_j(p) * r(p + o_j): 3-row sliding window of (x-1,x) / (x,x+1) / (x+1,x+2) pairs
+        {
+            u64 s1m, s2m, am, s1c, s2c, ac;
+            shifted(top, s1m, s2m); am = top;
+            shifted(A[1], s1c, s2c); ac = A[1];
+#pragma unroll
+            for (int i = 0; i < P; ++i) {
+                const u64 an = (i + 1 < P) ? A[i + 2] : bot;
+                u64 s1n, s2n;
+                shifted(an, s1n, s2n);
+                u64 acc = cc[i];
+                acc = fma2(nw[i][0], s1m, acc);
+                acc = fma2(nw[i][1], am, acc);
+                acc = fma2(nw[i][2], s2m, acc);
+                acc = fma2(nw[i][3], s1c, acc);
+                acc = fma2(nw[i][4], s2c, acc);
+                acc = fma2(nw[i][5], s1n, acc);
+                acc = fma2(nw[i][6], an, acc);
+                A[i] = fma2(nw[i][7], s2n, acc);
+                s1m = s1c; s2m = s2c; am = ac;
+                s1c = s1n; s2c = s2n; ac = an;
+            }
+        }
+        if (++t >= p.iters) {
+            // odd iteration count: move the rows back to slots 1..P for the epilogue
+#pragma unroll
+            for (int i = P; i >= 1; --i) A[i] = A[i - 1];
+            break;
+        }
+        // ===== odd step: rows in slots 0..P-1, bottom-up, never a refresh =====
+        *reinterpret_cast<u64*>(&sm.rowbuf[1][warp][0][2 * lane]) = A[0];
+        *reinterpret_cast<u64*>(&sm.rowbuf[1][warp][1][2 * lane]) = A[P - 1];
+        __syncthreads();
+        top = 0ull; bot = 0ull;
+        if (warp > 0) top = *reinterpret_cast<const u64*>(&sm.rowbuf[1][warp - 1][1][2 * lane]);
+        if (warp < NW - 1) bot = *reinterpret_cast<const u64*>(&sm.rowbuf[1][warp + 1][0][2 * lane]);
+        {
+            u64 s1p, s2p, ap, s1c, s2c, ac;
+            shifted(bot, s1p, s2p); ap = bot;
+            shifted(A[P - 1], s1c, s2c); ac = A[P - 1];
+#pragma unroll
+            for (int i = P - 1; i >= 0; --i) {
+                const u64 an = (i > 0) ? A[i - 1] : top;      // row i-1
+                u64 s1n, s2n;
+                shifted(an, s1n, s2n);
+                u64 acc = cc[i];
+                acc = fma2(nw[i][7], s2p, acc);
+                acc = fma2(nw[i][6], ap, acc);
+                acc = fma2(nw[i][5], s1p, acc);
+                acc = fma2(nw[i][4], s2c, acc);
+                acc = fma2(nw[i][3], s1c, acc);
+                acc = fma2(nw[i][2], s2n, acc);
+                acc = fma2(nw[i][1], an, acc);
+                A[i + 1] = fma2(nw[i][0], s1n, acc);
+                s1p = s1c; s2p = s2c; ap = ac;
+                s1c = s1n; s2c = s2n; ac = an;
+            }
+        }
+    }
+
+    // ---- epilogue: only the final depth goes back to HBM, and only from the pixels this CTA is authoritative for
+    const int vx0 = tix > 0 ? tix * p.stepx + p.margin : 0;
+    const int vx1 = tix == p.ntx - 1 ? W : tix * p.stepx + p.ew - p.margin;
+    const int vy0 = tiy > 0 ? tiy * p.stepy + p.margin : 0;
+    const int vy1 = tiy == p.nty - 1 ? H : tiy * p.stepy + p.eh - p.margin;
+    T* ob = p.out + (size_t)plane * hw;
+    if (lane_auth) {
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+            const int ty = warp * P + i, gy = gy0 + i;
+            if (ty < ry0 || ty > ry1 || gy < vy0 || gy >= vy1 || gy >= H) continue;
+            if (gx >= vx0 && gx < vx1 && gx < W) ob[(size_t)gy * W + gx] = from_f32<T>(lo_of(A[i + 1]));
+            if (gx + 1 >= vx0 && gx + 1 < vx1 && gx + 1 < W) ob[(size_t)gy * W + gx + 1] = from_f32<T>(hi_of(A[i + 1]));
+        }
+    }
+}
+
+// ---- host side: pick the cluster shape and the tiling ----------------------------------------------------
+constexpr int kP = 10, kNW = 8;               // 64 x 80 pixel register tile per CTA
+constexpr int kTH = kNW * kP, kStepY = kTH - 2 * kHaloY;
+
+struct Tiling { int cx, cy, ntx, nty, stepx, stepy, ew, eh; long ctas; bool ok; };
+
+inline int tiles_needed(int extent, int size, int margin, int* step)
+{
+    if (extent >= size) { *step = extent; return 1; }     // one tile reaches both image borders
+    const int s = extent - 2 * margin;
+    *step = s;
+    if (s <= 0) return -1;
+    // tile i covers [i*s, i*s + extent); the last one must reach the image border
+    int n = (size - extent + s - 1) / s + 1;
+    return n;
+}
+
+Tiling choose_tiling(int H, int W, int iters)
+{
+    Tiling best{}; best.ok = false; best.ctas = 0;
+    for (int cx = 1; cx <= 16; ++cx)
+        for (int cy = 1; cx * cy <= 16; ++cy) {
+            Tiling t{}; t.cx = cx; t.cy = cy;
+            t.ew = kStepX * (cx - 1) + kTileW; t.eh = kStepY * (cy - 1) + kTH;
+            t.ntx = tiles_needed(t.ew, W, iters, &t.stepx);
+            t.nty = tiles_needed(t.eh, H, iters, &t.stepy);
+            if (t.ntx < 0 || t.nty < 0) continue;
+            if ((t.stepx & 1) != 0) continue;             // keep pixel pairs at even x
+            t.ctas = (long)t.ntx * t.nty * cx * cy; t.ok = true;
+            // fewest CTAs wins; ties go to the smaller cluster (cheaper barrier, easier to place)
+            if (!best.ok || t.ctas < best.ctas || (t.ctas == best.ctas && cx * cy < best.cx * best.cy)) best = t;
+        }
+    return best;
+}
+
+template <typename T, int MODE>
+int launch(const FwdArgs<T>& a, const Tiling& tl)
+{
+    FusedParams<T> p{};
+    p.g = a.guidance; p.gbs = a.gbs; p.depth = a.depth; p.sparse = a.sparse; p.sparse_channels = a.sparse_channels; p.out = a.out;
+    p.C = a.C; p.H = a.H; p.W = a.W; p.iters = a.iters;
+    p.cx = tl.cx; p.cy = tl.cy; p.ntx = tl.ntx; p.nty = tl.nty; p.stepx = tl.stepx; p.stepy = tl.stepy; p.ew = tl.ew; p.eh = tl.eh;
+    p.margin = a.iters;
+    auto kern = fused3x3_kernel<T, kP, kNW, MODE>;
+    static thread_local bool attr_set[2] = {false, false};   // per (T, MODE) instantiation and host thread; cheap to repeat per device
+    (void)attr_set;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return (int)e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(tl.ntx * tl.cx), (unsigned)(tl.nty * tl.cy), (unsigned)(a.B * a.C));
+    cfg.blockDim = dim3(kNW * 32);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = a.stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)tl.cx; at[0].val.clusterDim.y = (unsigned)tl.cy; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kern, p);
+    if (e != cudaSuccess) return (int)e;
+    ++call_stats().launches;
+    return 0;
+}
+
+}  // namespace
+
+bool fused_supported(int C, int H, int W, int iters, int ksize, int mode)
+{
+    (void)C; (void)mode;
+    if (ksize != 3 || iters < 1) return false;
+    if ((long)H * W > (1l << 30)) return false;
+    return choose_tiling(H, W, iters).ok;
+}
+
+template <typename T>
+int fused_forward(const FwdArgs<T>& a)
+{
+    const Tiling tl = choose_tiling(a.H, a.W, a.iters);
+    if (!tl.ok) return CSPN_ERR_BAD_KERNEL_SIZE;
+    if ((long)a.B * a.C > 65535) return CSPN_ERR_BAD_SHAPE;
+    return a.mode == CSPN_MODE_NEW ? launch<T, CSPN_MODE_NEW>(a, tl) : launch<T, CSPN_MODE_OURS>(a, tl);
+}
+
 template int fused_forward<float>(const FwdArgs<float>&);
 template int fused_forward<__half>(const FwdArgs<__half>&);
-}
+
+}  // namespace cspn

@@ -75,8 +75,10 @@ __global__ void sweep_kernel(const float* __restrict__ nw, const TIn* __restrict
     float acc = 0.f;
     for (int k = 0; k < tt.n; ++k) {
         const int yy = y + tt.dy[k], xx = x + tt.dx[k];
-        if (yy >= 0 && yy < H && xx >= 0 && xx < W)
-            acc = fmaf(nb[k * hw], to_f32(rp[(size_t)yy * W + xx]), acc);
+        // out-of-image taps read the zero padding but are still multiplied: a pixel whose gathered weights
+        // are all zero has n_k = 0/0 and must come out NaN like the reference's 0/0 (CSPN_new.py:127)
+        const float rv = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? to_f32(rp[(size_t)yy * W + xx]) : 0.f;
+        acc = fmaf(nb[k * hw], rv, acc);
     }
     if (sparse) {
         const float m = signf(to_f32(sparse[((size_t)b * sparse_channels + (sparse_channels == 1 ? 0 : c)) * hw + p]));

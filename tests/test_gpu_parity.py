@@ -48,6 +48,22 @@ def _run(mode, g, d, s, iters, requires_grad=False, dtype=torch.float32):
     return y, tg, td
 
 
+_ORACLE_CACHE = {}
+
+
+def _oracle(key, g, d, s, iters, ksize, mode):
+    """C oracle on all host cores, memoised so the two CUDA paths share one CPU evaluation."""
+    if key not in _ORACLE_CACHE:
+        _ORACLE_CACHE[key] = c_oracle.forward(g, d, s, iters, ksize, mode, threads=0)
+    return _ORACLE_CACHE[key]
+
+
+def _atol(ref):
+    """1e-4 at the reference's depth scale of 10; grows with the value range (negative sparse entries make
+    the recurrence expansive: (1-m) = 2)."""
+    return FWD_ATOL * max(1.0, float(np.nanmax(np.abs(ref))) / 10.0)
+
+
 def _golden_names(golden):
     return sorted(n for n in golden if "guidance" in golden[n])
 
@@ -87,7 +103,7 @@ def test_nyu_known_answer_and_oracle(golden, path):
     g, d, s = nyu_golden_inputs()
     y, _, _ = _run(0, g, d, s, 24)
     assert_close_nan(y.cpu().numpy(), golden["A_nyu_seed304228_T24"]["out"], FWD_ATOL, "nyu golden")
-    assert_close_nan(y.cpu().numpy(), c_oracle.forward(g, d, s, 24, 3, 0), FWD_ATOL, "nyu oracle")
+    assert_close_nan(y.cpu().numpy(), _oracle("nyu", g, d, s, 24, 3, 0), FWD_ATOL, "nyu oracle")
 
 
 @pytest.mark.parametrize("path", PATHS)
@@ -107,9 +123,9 @@ def test_iteration_counts(path, iters):
     _lib.load().cspn_set_path(path)
     g, d, s = make_inputs(iters, 2, 8, 1, 50, 77, density=0.05)
     y, _, _ = _run(0, g, d, s, iters)
-    assert_close_nan(y.cpu().numpy(), c_oracle.forward(g, d, s, iters, 3, 0), FWD_ATOL, f"T={iters}")
+    assert_close_nan(y.cpu().numpy(), _oracle(("it", iters), g, d, s, iters, 3, 0), FWD_ATOL, f"T={iters}")
     y, _, _ = _run(0, g, d, None, iters)
-    assert_close_nan(y.cpu().numpy(), c_oracle.forward(g, d, None, iters, 3, 0), FWD_ATOL, f"T={iters} no sparse")
+    assert_close_nan(y.cpu().numpy(), _oracle(("it-ns", iters), g, d, None, iters, 3, 0), FWD_ATOL, f"T={iters} no sparse")
 
 
 def test_five_by_five_pac_variant():

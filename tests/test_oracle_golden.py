@@ -118,3 +118,17 @@ def test_masked_pixels_keep_blur_depth_not_sparse_value():
     y = c_oracle.forward(g, d, s, 5, 3, 0)
     hit = s > 0
     assert hit.any() and np.array_equal(y[hit], d[hit])       # CSPN_new.py:73,90 re-injects the BLUR depth
+
+
+def test_torch_port_matches_reference(golden):
+    """The op-for-op PyTorch port that bench.py times as the reference arm."""
+    import torch
+
+    from oracle import torch_port
+    for name in _names(golden):
+        case = golden[name]
+        mode, _, iters = case_config(name, case)
+        g, d = torch.from_numpy(case["guidance"]), torch.from_numpy(case["depth"])
+        s = torch.from_numpy(case["sparse"]) if "sparse" in case else None
+        y = torch_port.mode_a_forward(g, d, s, iters) if mode == 0 else torch_port.mode_b_forward(d, g, s, iters)
+        assert_close_nan(y.numpy(), case["out"], 1e-5 * max(1.0, float(np.nanmax(np.abs(case["depth"]))) / 10.0), name)
