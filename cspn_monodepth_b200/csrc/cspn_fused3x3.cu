@@ -12,16 +12,22 @@
 //    warps of a CTA exchange their edge rows through shared memory once per step.
 //  * A register-resident CTA tile is only 64 x (NW*P) pixels, far smaller than the T-pixel dependency cone,
 //    so CTAs cooperate as a thread-block CLUSTER (up to 16 CTAs, e.g. 5x3 = one whole 304x228 NYU image):
-//    every second step each CTA pushes a 2-pixel-deep halo ring into its neighbours' shared memory over
-//    DSMEM (st.shared::cluster) and the cluster barrier publishes it.  Only at the edge of a cluster tile
-//    that is not an image border does the classic shrinking (trapezoid) halo of T pixels apply.
+//    every second step each CTA pushes a 2-pixel-deep halo ring straight into its 8 neighbours' shared
+//    memory with st.async (DSMEM) and the neighbour's mbarrier counts the bytes - no cluster-wide barrier,
+//    no fence.  Only at the edge of a cluster tile that is not an image border does the classic shrinking
+//    (trapezoid) halo of T pixels apply.
+//  * The guidance tile (8 channels, 1-pixel apron) is staged once into shared memory by TMA
+//    (cp.async.bulk.tensor, one box per channel, out-of-image elements zero-filled by the hardware = the
+//    reference's ZeroPad2d), weights are normalised from there into registers; depth/sparse come in with
+//    plain coalesced loads that overlap the TMA.
 //  * HBM traffic is the algorithmic minimum: guidance/depth/sparse are read once (plus halo overlap that
 //    L2 serves), only the final depth is written.
-#include <cooperative_groups.h>
+#include <cuda.h>
+
+#include <cstddef>
+#include <cstring>
 
 #include "cspn_common.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace cspn {
 namespace {
@@ -34,6 +40,7 @@ constexpr int kHaloY = 2;             // two rows of halo per side between CTAs 
 constexpr int kPeriod = 2;            // halo refresh period in steps (= halo depth)
 constexpr int kStepX = kTileW - 2 * kHaloX;   // x spacing of CTA tiles inside a cluster (60)
 
+// ---- small PTX wrappers ------------------------------------------------------------------------------
 __device__ __forceinline__ u64 pk(float lo, float hi)
 {
     u64 d;
@@ -58,6 +65,49 @@ __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c)
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
     return d;
 }
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t cta_rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta_rank));
+    return r;
+}
+// 8-byte store into another CTA's shared memory; the bytes are counted on that CTA's mbarrier.
+__device__ __forceinline__ void st_async_b64(uint32_t remote_addr, u64 v, uint32_t remote_bar)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+                 :: "r"(remote_addr), "l"(v), "r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra WAIT_%=;\n\t}"
+        :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                 :: "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
 
 // (x-1,x) and (x+1,x+2) pairs of a row from its (x,x+1) pair: one shuffle + one register move each.
 __device__ __forceinline__ void shifted(u64 a, u64& s1, u64& s2)
@@ -81,26 +131,46 @@ struct FusedParams {
     int margin;           // decaying halo at cluster-tile edges that are not image borders (= iters)
 };
 
-// Shared memory of one CTA.  rowbuf: per-step edge rows of each warp (intra-CTA, double buffered by step
-// parity).  colbox/rowbox: the halo ring received from cluster neighbours (double buffered by refresh parity).
+// Static part of one CTA's shared memory.  rowbuf: per-step edge rows of each warp (intra-CTA, one buffer
+// per step parity).  colbox/rowbox: the halo ring received from cluster neighbours, double buffered by
+// refresh parity, each with its own transaction-counting mbarrier.
 template <int NW, int P>
-struct __align__(16) Smem {
+struct __align__(128) Smem {
     float rowbuf[2][NW][2][kTileW];
     float colbox[2][2][NW * P][2];        // [parity][side: 0 left, 1 right][tile row][2 px]
     float rowbox[2][2][kHaloY][kTileW];   // [parity][side: 0 top, 1 bottom][halo row][tile x]
+    u64 halo_bar[2];
+    u64 tma_bar[8];
 };
 
-template <typename T, int P, int NW, int MODE>
-__global__ void __launch_bounds__(NW * 32, 1) fused3x3_kernel(const __grid_constant__ FusedParams<T> p)
+// Geometry of the TMA staging buffer for the guidance tile.  The innermost start coordinate of a TMA box must
+// be 16-byte aligned in global memory (measured: anything else traps as an illegal instruction), so the box
+// starts at the aligned column at or left of (tile x - apron) and is wide enough for every sub-offset.
+template <typename T, int TH, int MODE>
+struct Stage {
+    static constexpr int apron = MODE == CSPN_MODE_NEW ? 1 : 0;       // mode NEW gathers weights from the 8 neighbours
+    static constexpr int rows = TH + 2 * apron;
+    static constexpr int align = 16 / (int)sizeof(T);                // elements per 16 bytes
+    static constexpr int cols = ((kTileW + 2 * apron + align - 1 + align - 1) / align) * align;   // fp32: 72 | 68, fp16: 80 | 72
+    static constexpr int box_bytes = rows * cols * (int)sizeof(T);   // what one TMA box delivers
+    static constexpr int plane = ((box_bytes + 127) / 128) * 128 / (int)sizeof(T);   // elements per channel, 128-byte aligned for TMA
+    static constexpr size_t bytes = (size_t)8 * plane * sizeof(T);
+    // aligned box start for a tile whose first pixel column is ox (floor division, ox - apron may be negative)
+    __host__ __device__ static int box_x(int ox) { const int v = ox - apron; return (v >= 0 ? v / align : -((-v + align - 1) / align)) * align; }
+};
+
+template <typename T, int P, int NW, int MODE, bool TMA>
+__global__ void __launch_bounds__(NW * 32, 1)
+fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant__ CUtensorMap gmap)
 {
     constexpr int TH = NW * P;
     constexpr int STEPY = TH - 2 * kHaloY;
-    __shared__ Smem<NW, P> sm;
+    using St = Stage<T, TH, MODE>;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    Smem<NW, P>& sm = *reinterpret_cast<Smem<NW, P>*>(smem_raw);
+    const T* stage = reinterpret_cast<const T*>(smem_raw + sizeof(Smem<NW, P>));
 
-    cg::cluster_group cluster = cg::this_cluster();
     const bool multi = p.cx * p.cy > 1;
-    if (multi) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");   // "I am running" (waited before the first push)
-
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ccx = blockIdx.x % p.cx, ccy = blockIdx.y % p.cy;
     const int tix = blockIdx.x / p.cx, tiy = blockIdx.y / p.cy;
@@ -109,11 +179,32 @@ __global__ void __launch_bounds__(NW * 32, 1) fused3x3_kernel(const __grid_const
     const int H = p.H, W = p.W;
     const size_t hw = (size_t)H * W;
 
-    // image coordinates of this thread's strip: columns gx, gx+1, rows gy0 .. gy0+P-1
-    const int gx = tix * p.stepx + ccx * kStepX + 2 * lane;
-    const int gy0 = tiy * p.stepy + ccy * STEPY + warp * P;
+    // image coordinates of this CTA tile / this thread's strip: columns gx, gx+1, rows gy0 .. gy0+P-1
+    const int ox = tix * p.stepx + ccx * kStepX, oy = tiy * p.stepy + ccy * STEPY;
+    const int gx = ox + 2 * lane;
+    const int gy0 = oy + warp * P;
 
-    const T* gb = p.g + (size_t)b * p.gbs;
+    // ---- barriers + TMA issue (one thread) --------------------------------------------------------------
+    if (threadIdx.x == 0) {
+        mbar_init(smem_u32(&sm.halo_bar[0]), 1);
+        mbar_init(smem_u32(&sm.halo_bar[1]), 1);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) mbar_init(smem_u32(&sm.tma_bar[k]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (TMA) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t bar = smem_u32(&sm.tma_bar[k]);
+                mbar_arrive_expect_tx(bar, (uint32_t)St::box_bytes);
+                tma_load_4d(smem_u32(stage + (size_t)k * St::plane), &gmap, bar, St::box_x(ox), oy - St::apron, k, b);
+            }
+        }
+    }
+    __syncthreads();
+    // "my barriers exist": neighbours may only push into this CTA after everyone passed the matching wait
+    if (multi) cluster_arrive();
+
     const T* db = p.depth + (size_t)plane * hw;
     const T* sb = p.sparse ? p.sparse + ((size_t)b * p.sparse_channels + (p.sparse_channels == 1 ? 0 : ch)) * hw : nullptr;
 
@@ -124,28 +215,85 @@ __global__ void __launch_bounds__(NW * 32, 1) fused3x3_kernel(const __grid_const
     // slot i before an odd one.  Even steps sweep top-down and write new row i into slot i (the slot old row
     // i-1 just vacated), odd steps sweep bottom-up and write into slot i+1 - no register copies between steps.
     u64 nw[P][8], cc[P], A[P + 1];
+    const bool x_in0 = gx >= 0 && gx < W, x_in1 = gx + 1 >= 0 && gx + 1 < W;
+    const bool vec_ok = (W & 1) == 0;        // pairs start at even x: 8-byte (fp32) / 4-byte (fp16) aligned when W is even
+
+    // depth and sparse first: plain coalesced loads in flight while the TMA boxes land
 #pragma unroll
     for (int i = 0; i < P; ++i) {
         const int gy = gy0 + i;
         const bool row_in = gy >= 0 && gy < H;
-        const bool in0 = row_in && gx >= 0 && gx < W, in1 = row_in && gx + 1 >= 0 && gx + 1 < W;
-        float w0[8], w1[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int jj = j < 4 ? j : j + 1;
-            const int dy = jj / 3 - 1, dx = jj % 3 - 1;
-            if (MODE == CSPN_MODE_NEW) {
-                const int k = 7 - j, yy = gy + dy, xx = gx + dx;
-                const bool rin = yy >= 0 && yy < H;
-                const T* src = gb + (size_t)k * hw + (size_t)yy * W + xx;
-                w0[j] = (rin && xx >= 0 && xx < W) ? fabsf(to_f32(src[0])) : 0.f;
-                w1[j] = (rin && xx + 1 >= 0 && xx + 1 < W) ? fabsf(to_f32(src[1])) : 0.f;
+        float d0 = 0.f, d1 = 0.f, m0 = 0.f, m1 = 0.f;
+        const size_t off = (size_t)gy * W + gx;
+        if (row_in && x_in0 && x_in1 && vec_ok) {
+            if (sizeof(T) == 4) {
+                const float2 v = *reinterpret_cast<const float2*>(db + off); d0 = v.x; d1 = v.y;
+                if (sb) { const float2 s = *reinterpret_cast<const float2*>(sb + off); m0 = signf(s.x); m1 = signf(s.y); }
             } else {
-                const T* src = gb + (size_t)j * hw + (size_t)gy * W + gx;
-                w0[j] = in0 ? to_f32(src[0]) : 0.f;
-                w1[j] = in1 ? to_f32(src[1]) : 0.f;
+                const float2 v = __half22float2(*reinterpret_cast<const __half2*>(db + off)); d0 = v.x; d1 = v.y;
+                if (sb) { const float2 s = __half22float2(*reinterpret_cast<const __half2*>(sb + off)); m0 = signf(s.x); m1 = signf(s.y); }
+            }
+        } else if (row_in) {
+            if (x_in0) { d0 = to_f32(db[off]); if (sb) m0 = signf(to_f32(sb[off])); }
+            if (x_in1) { d1 = to_f32(db[off + 1]); if (sb) m1 = signf(to_f32(sb[off + 1])); }
+        }
+        A[i + 1] = pk(d0, d1);
+        cc[i] = pk(m0, m1);                 // holds the mask until the weights are folded below
+    }
+    A[0] = 0ull;
+
+    // raw guidance values -> registers
+    if (TMA) {
+        const int x_off = ox - St::box_x(ox);           // column of the tile's first pixel inside the staged box
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            mbar_wait(smem_u32(&sm.tma_bar[k]), 0);
+            const T* sp = stage + (size_t)k * St::plane;
+            if (MODE == CSPN_MODE_NEW) {
+                const int j = 7 - k, jj = j < 4 ? j : j + 1;
+                const int dy = jj / 3 - 1, dx = jj % 3 - 1;
+#pragma unroll
+                for (int i = 0; i < P; ++i) {
+                    const T* src = sp + (warp * P + i + 1 + dy) * St::cols + x_off + 2 * lane + dx;
+                    nw[i][j] = pk(fabsf(to_f32(src[0])), fabsf(to_f32(src[1])));      // zero-filled outside the image
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < P; ++i) {
+                    const T* src = sp + (warp * P + i) * St::cols + x_off + 2 * lane;
+                    nw[i][k] = pk(to_f32(src[0]), to_f32(src[1]));
+                }
             }
         }
+    } else {
+        const T* gb = p.g + (size_t)b * p.gbs;
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+            const int gy = gy0 + i;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int jj = j < 4 ? j : j + 1;
+                const int dy = MODE == CSPN_MODE_NEW ? jj / 3 - 1 : 0, dx = MODE == CSPN_MODE_NEW ? jj % 3 - 1 : 0;
+                const int k = MODE == CSPN_MODE_NEW ? 7 - j : j, yy = gy + dy, xx = gx + dx;
+                const bool rin = yy >= 0 && yy < H;
+                const T* src = gb + (size_t)k * hw + (size_t)yy * W + xx;
+                float v0 = (rin && xx >= 0 && xx < W) ? to_f32(src[0]) : 0.f;
+                float v1 = (rin && xx + 1 >= 0 && xx + 1 < W) ? to_f32(src[1]) : 0.f;
+                if (MODE == CSPN_MODE_NEW) { v0 = fabsf(v0); v1 = fabsf(v1); }
+                nw[i][j] = pk(v0, v1);
+            }
+        }
+    }
+
+    // normalise, fold the sparse mask in
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+        const int gy = gy0 + i;
+        const bool row_in = gy >= 0 && gy < H;
+        const bool in0 = row_in && x_in0, in1 = row_in && x_in1;
+        float w0[8], w1[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { w0[j] = lo_of(nw[i][j]); w1[j] = hi_of(nw[i][j]); }
         if (MODE == CSPN_MODE_NEW) {
             float s0 = 0.f, s1 = 0.f;
 #pragma unroll
@@ -161,91 +309,99 @@ __global__ void __launch_bounds__(NW * 32, 1) fused3x3_kernel(const __grid_const
 #pragma unroll
             for (int j = 0; j < 8; ++j) { w0[j] = expf(w0[j] - m0); w1[j] = expf(w1[j] - m1); s0 += w0[j]; s1 += w1[j]; }
             const float i0 = __frcp_rn(s0), i1 = __frcp_rn(s1);
+            // taps that read the zero padding contribute n_j * 0 (no border renormalisation, pac.py:89): drop
+            // their weight instead, so that whatever a tile-edge shuffle delivers for them is multiplied by 0
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { w0[j] *= i0; w1[j] *= i1; }
+            for (int j = 0; j < 8; ++j) {
+                const int jj = j < 4 ? j : j + 1;
+                const int yy = gy + jj / 3 - 1, xx = gx + jj % 3 - 1;
+                const bool rin = yy >= 0 && yy < H;
+                w0[j] = (rin && xx >= 0 && xx < W) ? w0[j] * i0 : 0.f;
+                w1[j] = (rin && xx + 1 >= 0 && xx + 1 < W) ? w1[j] * i1 : 0.f;
+            }
         }
-        float d0 = 0.f, d1 = 0.f, m0 = 0.f, m1 = 0.f;
-        if (in0) { d0 = to_f32(db[(size_t)gy * W + gx]); if (sb) m0 = signf(to_f32(sb[(size_t)gy * W + gx])); }
-        if (in1) { d1 = to_f32(db[(size_t)gy * W + gx + 1]); if (sb) m1 = signf(to_f32(sb[(size_t)gy * W + gx + 1])); }
+        const float m0 = lo_of(cc[i]), m1 = hi_of(cc[i]);
         // pixels outside the image are virtual: zero weights, zero value (the reference's zero padding)
         const float f0 = in0 ? 1.f - m0 : 0.f, f1 = in1 ? 1.f - m1 : 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) nw[i][j] = pk(in0 ? f0 * w0[j] : 0.f, in1 ? f1 * w1[j] : 0.f);
-        cc[i] = pk(m0 * d0, m1 * d1);
-        A[i + 1] = pk(d0, d1);
+        cc[i] = pk(m0 * lo_of(A[i + 1]), m1 * hi_of(A[i + 1]));
     }
-    A[0] = 0ull;
 
     // which lanes / rows of this CTA tile are authoritative (not halo owned by a cluster neighbour)
     const int lx0 = has_left ? 1 : 0, lx1 = has_right ? 30 : 31;
     const int ry0 = has_up ? kHaloY : 0, ry1 = has_down ? TH - 1 - kHaloY : TH - 1;
     const bool lane_auth = lane >= lx0 && lane <= lx1;
-    const unsigned my_rank = cluster.block_rank();
+    const uint32_t my_rank = multi ? cluster_ctarank() : 0;
+    // bytes this CTA receives per refresh: 8 per (row | lane) message
+    const uint32_t expect_bytes = 8u * (uint32_t)(((has_left ? 1 : 0) + (has_right ? 1 : 0)) * (ry1 - ry0 + 1) +
+                                                  ((has_up ? 1 : 0) + (has_down ? 1 : 0)) * kHaloY * (lx1 - lx0 + 1) +
+                                                  kHaloY * (((has_up && has_left) ? 1 : 0) + ((has_up && has_right) ? 1 : 0) +
+                                                            ((has_down && has_left) ? 1 : 0) + ((has_down && has_right) ? 1 : 0)));
+    const uint32_t sm_base = smem_u32(&sm);
+    using SmemT = Smem<NW, P>;
+    constexpr uint32_t kColbox = offsetof(SmemT, colbox), kRowbox = offsetof(SmemT, rowbox), kHaloBar = offsetof(SmemT, halo_bar);
+    constexpr uint32_t kColPar = sizeof(float) * 2 * TH * 2, kColSide = sizeof(float) * TH * 2;
+    constexpr uint32_t kRowPar = sizeof(float) * 2 * kHaloY * kTileW, kRowSide = sizeof(float) * kHaloY * kTileW;
 
-    if (multi) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (multi) cluster_wait();
 
     // ---- T propagation steps ---------------------------------------------------------------------------
     for (int t = 0; t < p.iters; ++t) {
         // ===== even step: rows in slots 1..P, top-down =====
         const bool refresh = multi && t > 0;          // t is even here: halo ring (2 deep) is refreshed every 2 steps
-        const int rpar = (t / kPeriod) & 1;
+        const int e = t / kPeriod, rpar = e & 1;
         if (refresh) {
             // push the authoritative pixels that lie in a neighbour's halo ring into that neighbour's boxes
-            Smem<NW, P>* left = has_left ? cluster.map_shared_rank(&sm, my_rank - 1) : nullptr;
-            Smem<NW, P>* right = has_right ? cluster.map_shared_rank(&sm, my_rank + 1) : nullptr;
+            const uint32_t bar_off = kHaloBar + 8u * rpar;
             if (lane == 1 && has_left) {
+                const uint32_t nb = mapa(sm_base, my_rank - 1);
 #pragma unroll
                 for (int i = 0; i < P; ++i) {
                     const int ty = warp * P + i;
-                    if (ty >= ry0 && ty <= ry1) *reinterpret_cast<u64*>(&left->colbox[rpar][1][ty][0]) = A[i + 1];
+                    if (ty >= ry0 && ty <= ry1) st_async_b64(nb + kColbox + rpar * kColPar + kColSide + 8u * ty, A[i + 1], nb + bar_off);
                 }
             }
             if (lane == 30 && has_right) {
+                const uint32_t nb = mapa(sm_base, my_rank + 1);
 #pragma unroll
                 for (int i = 0; i < P; ++i) {
                     const int ty = warp * P + i;
-                    if (ty >= ry0 && ty <= ry1) *reinterpret_cast<u64*>(&right->colbox[rpar][0][ty][0]) = A[i + 1];
+                    if (ty >= ry0 && ty <= ry1) st_async_b64(nb + kColbox + rpar * kColPar + 8u * ty, A[i + 1], nb + bar_off);
                 }
             }
             if (has_up && warp == 0) {
                 // my tile rows kHaloY .. 2*kHaloY-1 are the upper neighbour's bottom halo rows
-                Smem<NW, P>* up = cluster.map_shared_rank(&sm, my_rank - p.cx);
-                Smem<NW, P>* upl = has_left ? cluster.map_shared_rank(&sm, my_rank - p.cx - 1) : nullptr;
-                Smem<NW, P>* upr = has_right ? cluster.map_shared_rank(&sm, my_rank - p.cx + 1) : nullptr;
+                const uint32_t up = mapa(sm_base, my_rank - p.cx);
 #pragma unroll
                 for (int h = 0; h < kHaloY; ++h) {
                     const u64 v = A[kHaloY + h + 1];
-                    if (lane_auth) *reinterpret_cast<u64*>(&up->rowbox[rpar][1][h][2 * lane]) = v;
-                    if (lane == 1 && has_left) *reinterpret_cast<u64*>(&upl->colbox[rpar][1][TH - kHaloY + h][0]) = v;
-                    if (lane == 30 && has_right) *reinterpret_cast<u64*>(&upr->colbox[rpar][0][TH - kHaloY + h][0]) = v;
+                    if (lane_auth) st_async_b64(up + kRowbox + rpar * kRowPar + kRowSide + 4u * (h * kTileW + 2 * lane), v, up + bar_off);
+                    if (lane == 1 && has_left) { const uint32_t nb = mapa(sm_base, my_rank - p.cx - 1); st_async_b64(nb + kColbox + rpar * kColPar + kColSide + 8u * (TH - kHaloY + h), v, nb + bar_off); }
+                    if (lane == 30 && has_right) { const uint32_t nb = mapa(sm_base, my_rank - p.cx + 1); st_async_b64(nb + kColbox + rpar * kColPar + 8u * (TH - kHaloY + h), v, nb + bar_off); }
                 }
             }
             if (has_down && warp == NW - 1) {
-                Smem<NW, P>* dn = cluster.map_shared_rank(&sm, my_rank + p.cx);
-                Smem<NW, P>* dnl = has_left ? cluster.map_shared_rank(&sm, my_rank + p.cx - 1) : nullptr;
-                Smem<NW, P>* dnr = has_right ? cluster.map_shared_rank(&sm, my_rank + p.cx + 1) : nullptr;
+                const uint32_t dn = mapa(sm_base, my_rank + p.cx);
 #pragma unroll
                 for (int h = 0; h < kHaloY; ++h) {
                     const u64 v = A[P - 2 * kHaloY + h + 1];
-                    if (lane_auth) *reinterpret_cast<u64*>(&dn->rowbox[rpar][0][h][2 * lane]) = v;
-                    if (lane == 1 && has_left) *reinterpret_cast<u64*>(&dnl->colbox[rpar][1][h][0]) = v;
-                    if (lane == 30 && has_right) *reinterpret_cast<u64*>(&dnr->colbox[rpar][0][h][0]) = v;
+                    if (lane_auth) st_async_b64(dn + kRowbox + rpar * kRowPar + 4u * (h * kTileW + 2 * lane), v, dn + bar_off);
+                    if (lane == 1 && has_left) { const uint32_t nb = mapa(sm_base, my_rank + p.cx - 1); st_async_b64(nb + kColbox + rpar * kColPar + kColSide + 8u * h, v, nb + bar_off); }
+                    if (lane == 30 && has_right) { const uint32_t nb = mapa(sm_base, my_rank + p.cx + 1); st_async_b64(nb + kColbox + rpar * kColPar + 8u * h, v, nb + bar_off); }
                 }
             }
+            if (threadIdx.x == 0) mbar_arrive_expect_tx(sm_base + bar_off, expect_bytes);
         }
         // publish this warp's edge rows for the warps above / below (same CTA)
         *reinterpret_cast<u64*>(&sm.rowbuf[0][warp][0][2 * lane]) = A[1];
         *reinterpret_cast<u64*>(&sm.rowbuf[0][warp][1][2 * lane]) = A[P];
-        if (refresh) {
-            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-            asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-        } else {
-            __syncthreads();
-        }
+        __syncthreads();
         u64 top = 0ull, bot = 0ull;   // rows -1 and P of this strip (zero above/below the CTA tile)
         if (warp > 0) top = *reinterpret_cast<const u64*>(&sm.rowbuf[0][warp - 1][1][2 * lane]);
         if (warp < NW - 1) bot = *reinterpret_cast<const u64*>(&sm.rowbuf[0][warp + 1][0][2 * lane]);
         if (refresh) {
+            mbar_wait(sm_base + kHaloBar + 8u * rpar, (uint32_t)(((e - 1) >> 1) & 1));
             if (has_up && warp == 0) {
 #pragma unroll
                 for (int h = 0; h < kHaloY; ++h) A[h + 1] = *reinterpret_cast<const u64*>(&sm.rowbox[rpar][0][h][2 * lane]);
@@ -331,12 +487,19 @@ __global__ void __launch_bounds__(NW * 32, 1) fused3x3_kernel(const __grid_const
     const int vy1 = tiy == p.nty - 1 ? H : tiy * p.stepy + p.eh - p.margin;
     T* ob = p.out + (size_t)plane * hw;
     if (lane_auth) {
+        const bool ok0 = gx >= vx0 && gx < vx1 && gx < W, ok1 = gx + 1 >= vx0 && gx + 1 < vx1 && gx + 1 < W;
 #pragma unroll
         for (int i = 0; i < P; ++i) {
             const int ty = warp * P + i, gy = gy0 + i;
             if (ty < ry0 || ty > ry1 || gy < vy0 || gy >= vy1 || gy >= H) continue;
-            if (gx >= vx0 && gx < vx1 && gx < W) ob[(size_t)gy * W + gx] = from_f32<T>(lo_of(A[i + 1]));
-            if (gx + 1 >= vx0 && gx + 1 < vx1 && gx + 1 < W) ob[(size_t)gy * W + gx + 1] = from_f32<T>(hi_of(A[i + 1]));
+            const size_t off = (size_t)gy * W + gx;
+            if (ok0 && ok1 && vec_ok) {
+                if (sizeof(T) == 4) *reinterpret_cast<float2*>(ob + off) = make_float2(lo_of(A[i + 1]), hi_of(A[i + 1]));
+                else *reinterpret_cast<__half2*>(ob + off) = __floats2half2_rn(lo_of(A[i + 1]), hi_of(A[i + 1]));
+            } else {
+                if (ok0) ob[off] = from_f32<T>(lo_of(A[i + 1]));
+                if (ok1) ob[off + 1] = from_f32<T>(hi_of(A[i + 1]));
+            }
         }
     }
 }
@@ -354,8 +517,7 @@ inline int tiles_needed(int extent, int size, int margin, int* step)
     *step = s;
     if (s <= 0) return -1;
     // tile i covers [i*s, i*s + extent); the last one must reach the image border
-    int n = (size - extent + s - 1) / s + 1;
-    return n;
+    return (size - extent + s - 1) / s + 1;
 }
 
 Tiling choose_tiling(int H, int W, int iters)
@@ -370,10 +532,66 @@ Tiling choose_tiling(int H, int W, int iters)
             if (t.ntx < 0 || t.nty < 0) continue;
             if ((t.stepx & 1) != 0) continue;             // keep pixel pairs at even x
             t.ctas = (long)t.ntx * t.nty * cx * cy; t.ok = true;
-            // fewest CTAs wins; ties go to the smaller cluster (cheaper barrier, easier to place)
+            // fewest CTAs wins; ties go to the smaller cluster (cheaper to place)
             if (!best.ok || t.ctas < best.ctas || (t.ctas == best.ctas && cx * cy < best.cx * best.cy)) best = t;
         }
     return best;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled()
+{
+    static EncodeTiledFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+        return (EncodeTiledFn)f;
+    }();
+    return fn;
+}
+
+// 4-D view (W, H, 8 channels, B) of the guidance tensor; box = one channel plane of the staging buffer.
+template <typename T, int MODE>
+bool make_guidance_map(const FwdArgs<T>& a, CUtensorMap* map)
+{
+    using St = Stage<T, kTH, MODE>;
+    const size_t es = sizeof(T);
+    if (!encode_tiled()) return false;
+    if (((uintptr_t)a.guidance & 15) || ((size_t)a.W * es) % 16 || ((size_t)a.gbs * es) % 16) return false;
+    const cuuint64_t dims[4] = {(cuuint64_t)a.W, (cuuint64_t)a.H, 8, (cuuint64_t)a.B};
+    const cuuint64_t strides[3] = {(cuuint64_t)a.W * es, (cuuint64_t)a.H * a.W * es, (cuuint64_t)a.gbs * es};
+    const cuuint32_t box[4] = {(cuuint32_t)St::cols, (cuuint32_t)St::rows, 1, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = encode_tiled()(map, es == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
+                                      const_cast<T*>(a.guidance), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+template <typename T, int MODE, bool TMA>
+int launch_variant(const FusedParams<T>& p, const CUtensorMap& map, const Tiling& tl, int planes, cudaStream_t stream)
+{
+    auto kern = fused3x3_kernel<T, kP, kNW, MODE, TMA>;
+    const size_t smem = sizeof(Smem<kNW, kP>) + (TMA ? Stage<T, kTH, MODE>::bytes : 0);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(tl.ntx * tl.cx), (unsigned)(tl.nty * tl.cy), (unsigned)planes);
+    cfg.blockDim = dim3(kNW * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)tl.cx; at[0].val.clusterDim.y = (unsigned)tl.cy; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kern, p, map);
+    if (e != cudaSuccess) return (int)e;
+    ++call_stats().launches;
+    return 0;
 }
 
 template <typename T, int MODE>
@@ -384,24 +602,10 @@ int launch(const FwdArgs<T>& a, const Tiling& tl)
     p.C = a.C; p.H = a.H; p.W = a.W; p.iters = a.iters;
     p.cx = tl.cx; p.cy = tl.cy; p.ntx = tl.ntx; p.nty = tl.nty; p.stepx = tl.stepx; p.stepy = tl.stepy; p.ew = tl.ew; p.eh = tl.eh;
     p.margin = a.iters;
-    auto kern = fused3x3_kernel<T, kP, kNW, MODE>;
-    static thread_local bool attr_set[2] = {false, false};   // per (T, MODE) instantiation and host thread; cheap to repeat per device
-    (void)attr_set;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    if (e != cudaSuccess) return (int)e;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(tl.ntx * tl.cx), (unsigned)(tl.nty * tl.cy), (unsigned)(a.B * a.C));
-    cfg.blockDim = dim3(kNW * 32);
-    cfg.dynamicSmemBytes = 0;
-    cfg.stream = a.stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = (unsigned)tl.cx; at[0].val.clusterDim.y = (unsigned)tl.cy; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, kern, p);
-    if (e != cudaSuccess) return (int)e;
-    ++call_stats().launches;
-    return 0;
+    alignas(64) CUtensorMap map;
+    memset(&map, 0, sizeof map);
+    if (make_guidance_map<T, MODE>(a, &map)) return launch_variant<T, MODE, true>(p, map, tl, a.B * a.C, a.stream);
+    return launch_variant<T, MODE, false>(p, map, tl, a.B * a.C, a.stream);   // unaligned guidance: plain-load prologue
 }
 
 }  // namespace

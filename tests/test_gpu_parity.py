@@ -112,7 +112,7 @@ def test_forward_vs_oracle_shape_grid(path, shape):
     _lib.load().cspn_set_path(path)
     b, h, w = shape
     for mode, cg in ((0, 8), (0, 12), (1, 8)):
-        g, d, s = make_inputs(h * w + mode, b, cg, 1, h, w, density=0.02, neg=(mode == 1))
+        g, d, s = make_inputs(h * w + mode, b, cg, 1, h, w, density=0.02)
         y, _, _ = _run(mode, g, d, s, 24)
         assert_close_nan(y.cpu().numpy(), c_oracle.forward(g, d, s, 24, 3, mode), FWD_ATOL, f"{shape} mode {mode} cg {cg}")
 
