@@ -49,10 +49,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
     objs = []
     procs = []
+    extra = ["-DCSPN_TRACE"] if os.environ.get("CSPN_TRACE") else []
     for src in sources():
         obj = os.path.join(LIBDIR, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
-        procs.append((src, subprocess.Popen([nvcc, *NVCC_FLAGS, "-c", src, "-o", obj], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        procs.append((src, subprocess.Popen([nvcc, *NVCC_FLAGS, *extra, "-c", src, "-o", obj], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for src, p in procs:
         out, _ = p.communicate()

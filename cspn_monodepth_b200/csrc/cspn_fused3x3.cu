@@ -26,6 +26,7 @@
 
 #include <cstddef>
 #include <cstring>
+#include <type_traits>
 
 #include "cspn_common.cuh"
 
@@ -65,6 +66,18 @@ __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c)
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
     return d;
 }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b)
+{
+    u64 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b)
+{
+    u64 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t cta_rank)
 {
@@ -78,6 +91,20 @@ __device__ __forceinline__ void st_async_b64(uint32_t remote_addr, u64 v, uint32
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
                  :: "r"(remote_addr), "l"(v), "r"(remote_bar) : "memory");
 }
+// Same, predicated: lanes with pred == false issue nothing (no divergent branch around the store).
+__device__ __forceinline__ void st_async_b64_if(bool pred, uint32_t remote_addr, u64 v, uint32_t remote_bar)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t"
+                 "@q st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];\n\t}"
+                 :: "r"(remote_addr), "l"(v), "r"(remote_bar), "r"((uint32_t)pred) : "memory");
+}
+// Bulk copy of `bytes` (multiple of 16) from this CTA's shared memory into a cluster neighbour's, counted on the
+// neighbour's mbarrier.  Runs on the async copy engine; the issuing thread does not wait.
+__device__ __forceinline__ void bulk_s2s(uint32_t remote_dst, uint32_t local_src, uint32_t bytes, uint32_t remote_bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(remote_dst), "r"(local_src), "r"(bytes), "r"(remote_bar) : "memory");
+}
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
@@ -86,12 +113,14 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
 }
+// Default (cta-scope acquire) semantics: in both uses the awaited bytes land in THIS CTA's shared memory and
+// are published by the barrier's complete_tx (TMA box / neighbours' st.async), like any TMA consumer.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
         "@!p bra WAIT_%=;\n\t}"
         :: "r"(bar), "r"(parity) : "memory");
 }
@@ -100,7 +129,10 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
                  :: "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
 }
-__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+// relaxed: the only thing published before it is mbarrier initialisation, which fence.mbarrier_init covers
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ float2 to_f32x2(float2 v) { return v; }
+__device__ __forceinline__ float2 to_f32x2(__half2 v) { return __half22float2(v); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t cluster_ctarank()
 {
@@ -117,6 +149,15 @@ __device__ __forceinline__ void shifted(u64 a, u64& s1, u64& s2)
     s1 = pk(l, lo);
     s2 = pk(hi, r);
 }
+
+// Optional cycle trace (build with -DCSPN_TRACE): lane 0 of every warp stamps clock64() at fixed points.
+#ifdef CSPN_TRACE
+__device__ long long* g_trace = nullptr;
+constexpr int kTraceSlots = 96;
+#define TRACE(slot) do { if (g_trace && (threadIdx.x & 31) == 0) g_trace[((size_t)(blockIdx.z * gridDim.y * gridDim.x + blockIdx.y * gridDim.x + blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kTraceSlots + (slot)] = clock64(); } while (0)
+#else
+#define TRACE(slot) do { } while (0)
+#endif
 
 template <typename T>
 struct FusedParams {
@@ -139,6 +180,7 @@ struct __align__(128) Smem {
     float rowbuf[2][NW][2][kTileW];
     float colbox[2][2][NW * P][2];        // [parity][side: 0 left, 1 right][tile row][2 px]
     float rowbox[2][2][kHaloY][kTileW];   // [parity][side: 0 top, 1 bottom][halo row][tile x]
+    u64 colstage[2][2][NW * P];           // [parity][side][tile row]: rim columns on their way to the left / right neighbour
     u64 halo_bar[2];
     u64 tma_bar[8];
 };
@@ -170,6 +212,7 @@ fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant_
     Smem<NW, P>& sm = *reinterpret_cast<Smem<NW, P>*>(smem_raw);
     const T* stage = reinterpret_cast<const T*>(smem_raw + sizeof(Smem<NW, P>));
 
+    TRACE(0);
     const bool multi = p.cx * p.cy > 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ccx = blockIdx.x % p.cx, ccy = blockIdx.y % p.cy;
@@ -201,6 +244,7 @@ fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant_
             }
         }
     }
+    TRACE(1);
     __syncthreads();
     // "my barriers exist": neighbours may only push into this CTA after everyone passed the matching wait
     if (multi) cluster_arrive();
@@ -211,43 +255,54 @@ fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant_
     // ---- prologue: loop-invariant weights n'_j = (1-m) * n_j, re-injection c = m*d0, r^0 = d0 -------------
     // internal tap order j: (dy,dx) row-major without the centre; mode NEW channel k = 7 - j reads the
     // guidance AT THE NEIGHBOUR p + o (CSPN_new.py:43-67), mode OURS channel j reads it at p (CSPN_ours.py:37-41).
-    // A holds the strip's P rows in P+1 register slots: row i lives in slot i+1 before an even step and in
-    // slot i before an odd one.  Even steps sweep top-down and write new row i into slot i (the slot old row
-    // i-1 just vacated), odd steps sweep bottom-up and write into slot i+1 - no register copies between steps.
-    u64 nw[P][8], cc[P], A[P + 1];
+    u64 nw[P][8], cc[P], A[P];
     const bool x_in0 = gx >= 0 && gx < W, x_in1 = gx + 1 >= 0 && gx + 1 < W;
     const bool vec_ok = (W & 1) == 0;        // pairs start at even x: 8-byte (fp32) / 4-byte (fp16) aligned when W is even
 
-    // depth and sparse first: plain coalesced loads in flight while the TMA boxes land
+    // depth and sparse first: plain coalesced loads, all issued back to back (clamped addresses, no branches
+    // between them) so that they are in flight together while the TMA boxes land
+    if (vec_ok) {
+        typedef typename std::conditional<sizeof(T) == 4, float2, __half2>::type V2;
+        const int cgx = min(max(gx, 0), W - 2);
+        V2 dv[P], sv[P];
 #pragma unroll
-    for (int i = 0; i < P; ++i) {
-        const int gy = gy0 + i;
-        const bool row_in = gy >= 0 && gy < H;
-        float d0 = 0.f, d1 = 0.f, m0 = 0.f, m1 = 0.f;
-        const size_t off = (size_t)gy * W + gx;
-        if (row_in && x_in0 && x_in1 && vec_ok) {
-            if (sizeof(T) == 4) {
-                const float2 v = *reinterpret_cast<const float2*>(db + off); d0 = v.x; d1 = v.y;
-                if (sb) { const float2 s = *reinterpret_cast<const float2*>(sb + off); m0 = signf(s.x); m1 = signf(s.y); }
-            } else {
-                const float2 v = __half22float2(*reinterpret_cast<const __half2*>(db + off)); d0 = v.x; d1 = v.y;
-                if (sb) { const float2 s = __half22float2(*reinterpret_cast<const __half2*>(sb + off)); m0 = signf(s.x); m1 = signf(s.y); }
-            }
-        } else if (row_in) {
-            if (x_in0) { d0 = to_f32(db[off]); if (sb) m0 = signf(to_f32(sb[off])); }
-            if (x_in1) { d1 = to_f32(db[off + 1]); if (sb) m1 = signf(to_f32(sb[off + 1])); }
+        for (int i = 0; i < P; ++i) {
+            const size_t off = (size_t)min(max(gy0 + i, 0), H - 1) * W + cgx;
+            dv[i] = *reinterpret_cast<const V2*>(db + off);
+            if (sb) sv[i] = *reinterpret_cast<const V2*>(sb + off);
         }
-        A[i + 1] = pk(d0, d1);
-        cc[i] = pk(m0, m1);                 // holds the mask until the weights are folded below
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+            const int gy = gy0 + i;
+            const bool in = gy >= 0 && gy < H && x_in0;        // W even and gx even: both pixels of the pair are in or out together
+            const float2 d = to_f32x2(dv[i]);
+            float2 m = make_float2(0.f, 0.f);
+            if (sb) { const float2 sp2 = to_f32x2(sv[i]); m = make_float2(signf(sp2.x), signf(sp2.y)); }
+            A[i] = in ? pk(d.x, d.y) : 0ull;
+            cc[i] = in ? pk(m.x, m.y) : 0ull;               // holds the mask until the weights are folded below
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+            const int gy = gy0 + i;
+            const bool row_in = gy >= 0 && gy < H;
+            float d0 = 0.f, d1 = 0.f, m0 = 0.f, m1 = 0.f;
+            const size_t off = (size_t)gy * W + gx;
+            if (row_in && x_in0) { d0 = to_f32(db[off]); if (sb) m0 = signf(to_f32(sb[off])); }
+            if (row_in && x_in1) { d1 = to_f32(db[off + 1]); if (sb) m1 = signf(to_f32(sb[off + 1])); }
+            A[i] = pk(d0, d1);
+            cc[i] = pk(m0, m1);
+        }
     }
-    A[0] = 0ull;
 
+    TRACE(2);
     // raw guidance values -> registers
     if (TMA) {
         const int x_off = ox - St::box_x(ox);           // column of the tile's first pixel inside the staged box
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             mbar_wait(smem_u32(&sm.tma_bar[k]), 0);
+            TRACE(3 + k);
             const T* sp = stage + (size_t)k * St::plane;
             if (MODE == CSPN_MODE_NEW) {
                 const int j = 7 - k, jj = j < 4 ? j : j + 1;
@@ -285,30 +340,45 @@ fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant_
         }
     }
 
-    // normalise, fold the sparse mask in
+    TRACE(11);
+    // normalise, fold the sparse mask in (packed f32x2 arithmetic, all rows' reductions independent)
+    if (MODE == CSPN_MODE_NEW) {
+        u64 scale[P];
 #pragma unroll
-    for (int i = 0; i < P; ++i) {
-        const int gy = gy0 + i;
-        const bool row_in = gy >= 0 && gy < H;
-        const bool in0 = row_in && x_in0, in1 = row_in && x_in1;
-        float w0[8], w1[8];
+        for (int i = 0; i < P; ++i) {
+            u64 sum = nw[i][7];                                       // reference order k = 0..7 (CSPN_new.py:124), k = 7 - j
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { w0[j] = lo_of(nw[i][j]); w1[j] = hi_of(nw[i][j]); }
-        if (MODE == CSPN_MODE_NEW) {
-            float s0 = 0.f, s1 = 0.f;
+            for (int k = 1; k < 8; ++k) sum = add2(sum, nw[i][7 - k]);
+            const int gy = gy0 + i;
+            const bool row_in = gy >= 0 && gy < H;
+            // n'_j = (1-m) * W_j / S.  S = 0 -> inf -> 0*inf = NaN like the reference's 0/0.  Pixels outside the
+            // image are virtual: exactly zero weights and value (the reference's zero padding).
+            const float f0 = (row_in && x_in0) ? (1.f - lo_of(cc[i])) * __frcp_rn(lo_of(sum)) : 0.f;
+            const float f1 = (row_in && x_in1) ? (1.f - hi_of(cc[i])) * __frcp_rn(hi_of(sum)) : 0.f;
+            scale[i] = pk(f0, f1);
+        }
 #pragma unroll
-            for (int k = 0; k < 8; ++k) { s0 += w0[7 - k]; s1 += w1[7 - k]; }     // reference order k = 0..7 (CSPN_new.py:124)
-            const float i0 = __frcp_rn(s0), i1 = __frcp_rn(s1);                   // S = 0 -> inf -> 0*inf = NaN like 0/0
+        for (int i = 0; i < P; ++i) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { w0[j] *= i0; w1[j] *= i1; }
-        } else {
+            for (int j = 0; j < 8; ++j) nw[i][j] = mul2(nw[i][j], scale[i]);
+            cc[i] = mul2(cc[i], A[i]);                                // c = m * d0
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+            const int gy = gy0 + i;
+            const bool row_in = gy >= 0 && gy < H;
+            const bool in0 = row_in && x_in0, in1 = row_in && x_in1;
+            float w0[8], w1[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { w0[j] = lo_of(nw[i][j]); w1[j] = hi_of(nw[i][j]); }
             float m0 = w0[0], m1 = w1[0];
 #pragma unroll
             for (int j = 1; j < 8; ++j) { m0 = fmaxf(m0, w0[j]); m1 = fmaxf(m1, w1[j]); }
             float s0 = 0.f, s1 = 0.f;
 #pragma unroll
             for (int j = 0; j < 8; ++j) { w0[j] = expf(w0[j] - m0); w1[j] = expf(w1[j] - m1); s0 += w0[j]; s1 += w1[j]; }
-            const float i0 = __frcp_rn(s0), i1 = __frcp_rn(s1);
+            const float f0 = in0 ? (1.f - lo_of(cc[i])) * __frcp_rn(s0) : 0.f, f1 = in1 ? (1.f - hi_of(cc[i])) * __frcp_rn(s1) : 0.f;
             // taps that read the zero padding contribute n_j * 0 (no border renormalisation, pac.py:89): drop
             // their weight instead, so that whatever a tile-edge shuffle delivers for them is multiplied by 0
 #pragma unroll
@@ -316,16 +386,10 @@ fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant_
                 const int jj = j < 4 ? j : j + 1;
                 const int yy = gy + jj / 3 - 1, xx = gx + jj % 3 - 1;
                 const bool rin = yy >= 0 && yy < H;
-                w0[j] = (rin && xx >= 0 && xx < W) ? w0[j] * i0 : 0.f;
-                w1[j] = (rin && xx + 1 >= 0 && xx + 1 < W) ? w1[j] * i1 : 0.f;
+                nw[i][j] = pk((rin && xx >= 0 && xx < W) ? w0[j] * f0 : 0.f, (rin && xx + 1 >= 0 && xx + 1 < W) ? w1[j] * f1 : 0.f);
             }
+            cc[i] = mul2(cc[i], A[i]);
         }
-        const float m0 = lo_of(cc[i]), m1 = hi_of(cc[i]);
-        // pixels outside the image are virtual: zero weights, zero value (the reference's zero padding)
-        const float f0 = in0 ? 1.f - m0 : 0.f, f1 = in1 ? 1.f - m1 : 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) nw[i][j] = pk(in0 ? f0 * w0[j] : 0.f, in1 ? f1 * w1[j] : 0.f);
-        cc[i] = pk(m0 * lo_of(A[i + 1]), m1 * hi_of(A[i + 1]));
     }
 
     // which lanes / rows of this CTA tile are authoritative (not halo owned by a cluster neighbour)
@@ -333,9 +397,10 @@ fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant_
     const int ry0 = has_up ? kHaloY : 0, ry1 = has_down ? TH - 1 - kHaloY : TH - 1;
     const bool lane_auth = lane >= lx0 && lane <= lx1;
     const uint32_t my_rank = multi ? cluster_ctarank() : 0;
-    // bytes this CTA receives per refresh: 8 per (row | lane) message
+    // bytes this CTA receives per refresh: 8 per row from the left / right neighbour, whole rows (all 32 lanes; halo
+    // lanes of a row are overridden by the column boxes) from above / below, 2x8 from each diagonal neighbour
     const uint32_t expect_bytes = 8u * (uint32_t)(((has_left ? 1 : 0) + (has_right ? 1 : 0)) * (ry1 - ry0 + 1) +
-                                                  ((has_up ? 1 : 0) + (has_down ? 1 : 0)) * kHaloY * (lx1 - lx0 + 1) +
+                                                  ((has_up ? 1 : 0) + (has_down ? 1 : 0)) * kHaloY * 32 +
                                                   kHaloY * (((has_up && has_left) ? 1 : 0) + ((has_up && has_right) ? 1 : 0) +
                                                             ((has_down && has_left) ? 1 : 0) + ((has_down && has_right) ? 1 : 0)));
     const uint32_t sm_base = smem_u32(&sm);
@@ -344,142 +409,167 @@ fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant_
     constexpr uint32_t kColPar = sizeof(float) * 2 * TH * 2, kColSide = sizeof(float) * TH * 2;
     constexpr uint32_t kRowPar = sizeof(float) * 2 * kHaloY * kTileW, kRowSide = sizeof(float) * kHaloY * kTileW;
 
+    TRACE(12);
     if (multi) cluster_wait();
+    TRACE(13);
 
     // ---- T propagation steps ---------------------------------------------------------------------------
-    for (int t = 0; t < p.iters; ++t) {
-        // ===== even step: rows in slots 1..P, top-down =====
-        const bool refresh = multi && t > 0;          // t is even here: halo ring (2 deep) is refreshed every 2 steps
-        const int e = t / kPeriod, rpar = e & 1;
-        if (refresh) {
-            // push the authoritative pixels that lie in a neighbour's halo ring into that neighbour's boxes
-            const uint32_t bar_off = kHaloBar + 8u * rpar;
-            if (lane == 1 && has_left) {
-                const uint32_t nb = mapa(sm_base, my_rank - 1);
+    // Steps come in pairs.  The halo ring received from cluster neighbours is 2 pixels deep, so it is refreshed
+    // at the start of every even step t >= 2; the values it needs (r^t on the rim of each CTA's authoritative
+    // region) are final during the odd step t-1 and are pushed from inside that step's compute phase, row by
+    // row as they complete, so the DSMEM latency hides behind the rest of the step.
+    const bool push_l = multi && lane == 1 && has_left, push_r = multi && lane == 30 && has_right;
+    // Per-lane message of the column push (parity 0 addresses; msg_dst == 0: this lane sends nothing):
+    //   lanes 0..P-1      row i of the left rim column  -> left neighbour's right box
+    //   lanes P..2P-1     row i of the right rim column -> right neighbour's left box
+    //   lanes 2P..2P+3    (top warp)    rows kHaloY.. of the rim columns -> upper-left / upper-right neighbour, bottom box rows
+    //   lanes 2P+4..2P+7  (bottom warp) rows TH-2*kHaloY.. of the rim columns -> lower-left / lower-right neighbour, top box rows
+    static_assert(2 * P + 4 * kHaloY <= 32, "column push needs one lane per message");
+    uint32_t msg_dst = 0u, msg_src = 0u, msg_bar = 0u;
+    if (multi) {
+        const int ty0 = warp * P;
+        int side = -1, srow = 0, drow = 0, dcy = 0;               // side: 0 = my left rim column, 1 = my right rim column
+        if (lane < 2 * P) {
+            side = lane / P; srow = drow = ty0 + lane % P;
+            if (srow < ry0 || srow > ry1) side = -1;
+        } else if (lane < 2 * P + 2 * kHaloY) {
+            if (warp == 0 && has_up) { side = (lane - 2 * P) / kHaloY; const int h = (lane - 2 * P) % kHaloY; srow = kHaloY + h; drow = TH - kHaloY + h; dcy = -1; }
+        } else if (lane < 2 * P + 4 * kHaloY) {
+            if (warp == NW - 1 && has_down) { side = (lane - 2 * P - 2 * kHaloY) / kHaloY; const int h = (lane - 2 * P - 2 * kHaloY) % kHaloY; srow = TH - 2 * kHaloY + h; drow = h; dcy = 1; }
+        }
+        if (side == 0 && !has_left) side = -1;
+        if (side == 1 && !has_right) side = -1;
+        if (side >= 0) {
+            const uint32_t nb = mapa(sm_base, my_rank + dcy * p.cx + (side == 0 ? -1 : 1));
+            msg_dst = nb + kColbox + (side == 0 ? kColSide : 0u) + 8u * drow;          // my left rim lands in the neighbour's RIGHT box
+            msg_bar = nb + kHaloBar;
+            msg_src = (uint32_t)(side * TH + srow) * 8u;
+        }
+    }
+
+    auto exchange_rows = [&](int par, u64& top, u64& bot) {
+        // publish this warp's edge rows for the warps above / below (same CTA), fetch theirs
+        *reinterpret_cast<u64*>(&sm.rowbuf[par][warp][0][2 * lane]) = A[0];
+        *reinterpret_cast<u64*>(&sm.rowbuf[par][warp][1][2 * lane]) = A[P - 1];
+        __syncthreads();
+        top = 0ull; bot = 0ull;   // rows -1 and P of this strip (zero above/below the CTA tile)
+        if (warp > 0) top = *reinterpret_cast<const u64*>(&sm.rowbuf[par][warp - 1][1][2 * lane]);
+        if (warp < NW - 1) bot = *reinterpret_cast<const u64*>(&sm.rowbuf[par][warp + 1][0][2 * lane]);
+    };
+
+    // One step, r'(p) = c(p) + sum_j n'_j(p) * r(p + o_j), organised by SOURCE row: row r's three pixel pairs
+    // (x-1,x) / (x,x+1) / (x+1,x+2) are formed once and scattered into the accumulators of output rows
+    // r+1 (taps 0-2), r (taps 3,4) and r-1 (taps 5-7).  Three independent FMA chains are in flight, only one
+    // row of shifted pairs is live, and output row r-1 completes exactly when old row r-1 is dead, so the
+    // update is in place (no second copy of the strip).  PUSH: also send finished rim values to the neighbours.
+    auto compute_step = [&](auto push_tag, u64 top, u64 bot, int rpar) {
+        constexpr bool PUSH = decltype(push_tag)::value;
+        const uint32_t bar_off = kHaloBar + 8u * rpar;
+        u64 acc[P];
 #pragma unroll
-                for (int i = 0; i < P; ++i) {
+        for (int r = -1; r <= P; ++r) {
+            const u64 src = r < 0 ? top : (r < P ? A[r < 0 ? 0 : (r < P ? r : 0)] : bot);
+            u64 s1, s2;
+            shifted(src, s1, s2);
+            if (r + 1 < P) {
+                u64 a = cc[r + 1];
+                a = fma2(nw[r + 1][0], s1, a);
+                a = fma2(nw[r + 1][1], src, a);
+                acc[r + 1] = fma2(nw[r + 1][2], s2, a);
+            }
+            if (r >= 0 && r < P) {
+                u64 a = acc[r];
+                a = fma2(nw[r][3], s1, a);
+                acc[r] = fma2(nw[r][4], s2, a);
+            }
+            if (r >= 1) {
+                const int i = r - 1;
+                u64 a = acc[i];
+                a = fma2(nw[i][5], s1, a);
+                a = fma2(nw[i][6], src, a);
+                a = fma2(nw[i][7], s2, a);
+                A[i] = a;
+                if (PUSH) {
+                    // stage the rim values locally (predicated stores, no branches); shipped in bulk after the sweep
                     const int ty = warp * P + i;
-                    if (ty >= ry0 && ty <= ry1) st_async_b64(nb + kColbox + rpar * kColPar + kColSide + 8u * ty, A[i + 1], nb + bar_off);
+                    if (push_l) sm.colstage[rpar][0][ty] = a;
+                    if (push_r) sm.colstage[rpar][1][ty] = a;
                 }
             }
-            if (lane == 30 && has_right) {
-                const uint32_t nb = mapa(sm_base, my_rank + 1);
-#pragma unroll
-                for (int i = 0; i < P; ++i) {
-                    const int ty = warp * P + i;
-                    if (ty >= ry0 && ty <= ry1) st_async_b64(nb + kColbox + rpar * kColPar + 8u * ty, A[i + 1], nb + bar_off);
-                }
+        }
+        if (PUSH) {
+            TRACE(90);
+            // ship: the warp's rim columns were staged by lanes 1 / 30; now lane m sends message m (one 8-byte
+            // st.async each, a single warp-wide instruction), rim rows go out directly from all 32 lanes
+            __syncwarp();
+            if (msg_dst != 0u) {
+                const u64 v = *reinterpret_cast<const u64*>(reinterpret_cast<const unsigned char*>(&sm.colstage[rpar][0][0]) + msg_src);
+                st_async_b64(msg_dst + rpar * kColPar, v, msg_bar + 8u * rpar);
             }
-            if (has_up && warp == 0) {
+            TRACE(91);
+            if (has_up && warp == 0) {                                                   // warp-uniform
                 // my tile rows kHaloY .. 2*kHaloY-1 are the upper neighbour's bottom halo rows
-                const uint32_t up = mapa(sm_base, my_rank - p.cx);
+                const uint32_t d = mapa(sm_base, my_rank - p.cx);
 #pragma unroll
-                for (int h = 0; h < kHaloY; ++h) {
-                    const u64 v = A[kHaloY + h + 1];
-                    if (lane_auth) st_async_b64(up + kRowbox + rpar * kRowPar + kRowSide + 4u * (h * kTileW + 2 * lane), v, up + bar_off);
-                    if (lane == 1 && has_left) { const uint32_t nb = mapa(sm_base, my_rank - p.cx - 1); st_async_b64(nb + kColbox + rpar * kColPar + kColSide + 8u * (TH - kHaloY + h), v, nb + bar_off); }
-                    if (lane == 30 && has_right) { const uint32_t nb = mapa(sm_base, my_rank - p.cx + 1); st_async_b64(nb + kColbox + rpar * kColPar + 8u * (TH - kHaloY + h), v, nb + bar_off); }
-                }
+                for (int h = 0; h < kHaloY; ++h)
+                    st_async_b64(d + kRowbox + rpar * kRowPar + kRowSide + 4u * (h * kTileW + 2 * lane), A[kHaloY + h], d + bar_off);
             }
             if (has_down && warp == NW - 1) {
-                const uint32_t dn = mapa(sm_base, my_rank + p.cx);
+                const uint32_t d = mapa(sm_base, my_rank + p.cx);
 #pragma unroll
-                for (int h = 0; h < kHaloY; ++h) {
-                    const u64 v = A[P - 2 * kHaloY + h + 1];
-                    if (lane_auth) st_async_b64(dn + kRowbox + rpar * kRowPar + 4u * (h * kTileW + 2 * lane), v, dn + bar_off);
-                    if (lane == 1 && has_left) { const uint32_t nb = mapa(sm_base, my_rank + p.cx - 1); st_async_b64(nb + kColbox + rpar * kColPar + kColSide + 8u * h, v, nb + bar_off); }
-                    if (lane == 30 && has_right) { const uint32_t nb = mapa(sm_base, my_rank + p.cx + 1); st_async_b64(nb + kColbox + rpar * kColPar + 8u * h, v, nb + bar_off); }
-                }
+                for (int h = 0; h < kHaloY; ++h)
+                    st_async_b64(d + kRowbox + rpar * kRowPar + 4u * (h * kTileW + 2 * lane), A[P - 2 * kHaloY + h], d + bar_off);
             }
-            if (threadIdx.x == 0) mbar_arrive_expect_tx(sm_base + bar_off, expect_bytes);
+            TRACE(92);
         }
-        // publish this warp's edge rows for the warps above / below (same CTA)
-        *reinterpret_cast<u64*>(&sm.rowbuf[0][warp][0][2 * lane]) = A[1];
-        *reinterpret_cast<u64*>(&sm.rowbuf[0][warp][1][2 * lane]) = A[P];
-        __syncthreads();
-        u64 top = 0ull, bot = 0ull;   // rows -1 and P of this strip (zero above/below the CTA tile)
-        if (warp > 0) top = *reinterpret_cast<const u64*>(&sm.rowbuf[0][warp - 1][1][2 * lane]);
-        if (warp < NW - 1) bot = *reinterpret_cast<const u64*>(&sm.rowbuf[0][warp + 1][0][2 * lane]);
-        if (refresh) {
+    };
+
+    for (int t = 0; t < p.iters; t += 2) {
+        // ===== even step t =====
+        const int e = t / kPeriod, rpar = e & 1;
+        u64 top, bot;
+        if (t < 24) TRACE(16 + 3 * t);
+        exchange_rows(0, top, bot);
+        if (t < 24) TRACE(17 + 3 * t);
+        if (multi && t > 0) {
+            // take the refreshed halo ring (pushed by the neighbours during their step t-1)
             mbar_wait(sm_base + kHaloBar + 8u * rpar, (uint32_t)(((e - 1) >> 1) & 1));
             if (has_up && warp == 0) {
 #pragma unroll
-                for (int h = 0; h < kHaloY; ++h) A[h + 1] = *reinterpret_cast<const u64*>(&sm.rowbox[rpar][0][h][2 * lane]);
+                for (int h = 0; h < kHaloY; ++h) A[h] = *reinterpret_cast<const u64*>(&sm.rowbox[rpar][0][h][2 * lane]);
             }
             if (has_down && warp == NW - 1) {
 #pragma unroll
-                for (int h = 0; h < kHaloY; ++h) A[P - kHaloY + h + 1] = *reinterpret_cast<const u64*>(&sm.rowbox[rpar][1][h][2 * lane]);
+                for (int h = 0; h < kHaloY; ++h) A[P - kHaloY + h] = *reinterpret_cast<const u64*>(&sm.rowbox[rpar][1][h][2 * lane]);
             }
             const bool edge = (lane == 0 && has_left) || (lane == 31 && has_right);
             if (edge) {
                 const int side = lane == 0 ? 0 : 1;
                 const int ty0 = warp * P;
 #pragma unroll
-                for (int i = 0; i < P; ++i) A[i + 1] = *reinterpret_cast<const u64*>(&sm.colbox[rpar][side][ty0 + i][0]);
+                for (int i = 0; i < P; ++i) A[i] = *reinterpret_cast<const u64*>(&sm.colbox[rpar][side][ty0 + i][0]);
                 top = ty0 > 0 ? *reinterpret_cast<const u64*>(&sm.colbox[rpar][side][ty0 - 1][0]) : 0ull;
                 bot = ty0 + P < TH ? *reinterpret_cast<const u64*>(&sm.colbox[rpar][side][ty0 + P][0]) : 0ull;
             }
         }
-        // r'(p) = c(p) + sum_j n'_j(p) * r(p + o_j): 3-row sliding window of (x-1,x) / (x,x+1) / (x+1,x+2) pairs
-        {
-            u64 s1m, s2m, am, s1c, s2c, ac;
-            shifted(top, s1m, s2m); am = top;
-            shifted(A[1], s1c, s2c); ac = A[1];
-#pragma unroll
-            for (int i = 0; i < P; ++i) {
-                const u64 an = (i + 1 < P) ? A[i + 2] : bot;
-                u64 s1n, s2n;
-                shifted(an, s1n, s2n);
-                u64 acc = cc[i];
-                acc = fma2(nw[i][0], s1m, acc);
-                acc = fma2(nw[i][1], am, acc);
-                acc = fma2(nw[i][2], s2m, acc);
-                acc = fma2(nw[i][3], s1c, acc);
-                acc = fma2(nw[i][4], s2c, acc);
-                acc = fma2(nw[i][5], s1n, acc);
-                acc = fma2(nw[i][6], an, acc);
-                A[i] = fma2(nw[i][7], s2n, acc);
-                s1m = s1c; s2m = s2c; am = ac;
-                s1c = s1n; s2c = s2n; ac = an;
-            }
-        }
-        if (++t >= p.iters) {
-            // odd iteration count: move the rows back to slots 1..P for the epilogue
-#pragma unroll
-            for (int i = P; i >= 1; --i) A[i] = A[i - 1];
-            break;
-        }
-        // ===== odd step: rows in slots 0..P-1, bottom-up, never a refresh =====
-        *reinterpret_cast<u64*>(&sm.rowbuf[1][warp][0][2 * lane]) = A[0];
-        *reinterpret_cast<u64*>(&sm.rowbuf[1][warp][1][2 * lane]) = A[P - 1];
-        __syncthreads();
-        top = 0ull; bot = 0ull;
-        if (warp > 0) top = *reinterpret_cast<const u64*>(&sm.rowbuf[1][warp - 1][1][2 * lane]);
-        if (warp < NW - 1) bot = *reinterpret_cast<const u64*>(&sm.rowbuf[1][warp + 1][0][2 * lane]);
-        {
-            u64 s1p, s2p, ap, s1c, s2c, ac;
-            shifted(bot, s1p, s2p); ap = bot;
-            shifted(A[P - 1], s1c, s2c); ac = A[P - 1];
-#pragma unroll
-            for (int i = P - 1; i >= 0; --i) {
-                const u64 an = (i > 0) ? A[i - 1] : top;      // row i-1
-                u64 s1n, s2n;
-                shifted(an, s1n, s2n);
-                u64 acc = cc[i];
-                acc = fma2(nw[i][7], s2p, acc);
-                acc = fma2(nw[i][6], ap, acc);
-                acc = fma2(nw[i][5], s1p, acc);
-                acc = fma2(nw[i][4], s2c, acc);
-                acc = fma2(nw[i][3], s1c, acc);
-                acc = fma2(nw[i][2], s2n, acc);
-                acc = fma2(nw[i][1], an, acc);
-                A[i + 1] = fma2(nw[i][0], s1n, acc);
-                s1p = s1c; s2p = s2c; ap = ac;
-                s1c = s1n; s2c = s2n; ac = an;
-            }
+        if (t < 24) TRACE(18 + 3 * t);
+        compute_step(std::false_type{}, top, bot, 0);
+        if (t + 1 >= p.iters) break;
+        // ===== odd step t+1: its results feed the refresh at step t+2 =====
+        if (t < 23) TRACE(16 + 3 * (t + 1));
+        exchange_rows(1, top, bot);
+        if (t < 23) { TRACE(17 + 3 * (t + 1)); TRACE(18 + 3 * (t + 1)); }
+        if (multi && t + 2 < p.iters) {
+            const int rnext = (e + 1) & 1;
+            if (threadIdx.x == 0) mbar_arrive_expect_tx(sm_base + kHaloBar + 8u * rnext, expect_bytes);
+            TRACE(89);
+            compute_step(std::true_type{}, top, bot, rnext);
+        } else {
+            compute_step(std::false_type{}, top, bot, 0);
         }
     }
 
+    TRACE(14);
     // ---- epilogue: only the final depth goes back to HBM, and only from the pixels this CTA is authoritative for
     const int vx0 = tix > 0 ? tix * p.stepx + p.margin : 0;
     const int vx1 = tix == p.ntx - 1 ? W : tix * p.stepx + p.ew - p.margin;
@@ -494,14 +584,15 @@ fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant_
             if (ty < ry0 || ty > ry1 || gy < vy0 || gy >= vy1 || gy >= H) continue;
             const size_t off = (size_t)gy * W + gx;
             if (ok0 && ok1 && vec_ok) {
-                if (sizeof(T) == 4) *reinterpret_cast<float2*>(ob + off) = make_float2(lo_of(A[i + 1]), hi_of(A[i + 1]));
-                else *reinterpret_cast<__half2*>(ob + off) = __floats2half2_rn(lo_of(A[i + 1]), hi_of(A[i + 1]));
+                if (sizeof(T) == 4) *reinterpret_cast<float2*>(ob + off) = make_float2(lo_of(A[i]), hi_of(A[i]));
+                else *reinterpret_cast<__half2*>(ob + off) = __floats2half2_rn(lo_of(A[i]), hi_of(A[i]));
             } else {
-                if (ok0) ob[off] = from_f32<T>(lo_of(A[i + 1]));
-                if (ok1) ob[off + 1] = from_f32<T>(hi_of(A[i + 1]));
+                if (ok0) ob[off] = from_f32<T>(lo_of(A[i]));
+                if (ok1) ob[off + 1] = from_f32<T>(hi_of(A[i]));
             }
         }
     }
+    TRACE(15);
 }
 
 // ---- host side: pick the cluster shape and the tiling ----------------------------------------------------
@@ -609,6 +700,14 @@ int launch(const FwdArgs<T>& a, const Tiling& tl)
 }
 
 }  // namespace
+
+#ifdef CSPN_TRACE
+extern "C" __attribute__((visibility("default"))) int cspn_debug_set_trace(void* buf)
+{
+    long long* ptr = (long long*)buf;
+    return (int)cudaMemcpyToSymbol(g_trace, &ptr, sizeof ptr);
+}
+#endif
 
 bool fused_supported(int C, int H, int W, int iters, int ksize, int mode)
 {
