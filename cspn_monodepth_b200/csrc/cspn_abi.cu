@@ -178,7 +178,7 @@ size_t cspn_fwd_workspace_bytes(int B, int C, int H, int W, int iters, int ksize
 {
     TapTable tt;
     if (!make_taps(mode, ksize, &tt) || B < 1 || C < 1 || H < 1 || W < 1 || iters < 1) return 0;
-    if (use_fused(C, H, W, iters, ksize, mode, nullptr)) return 0;
+    if (use_fused(C, H, W, iters, ksize, mode, nullptr)) return fused_workspace(B, C, H, W, iters);
     return generic_fwd_workspace(B, C, H, W, tt.n);
 }
 

@@ -83,5 +83,6 @@ template <typename T> int generic_backward(const BwdArgs<T>& a, const TapTable& 
 // fused path (cspn_fused3x3.cu): whole recurrence in one launch, 3x3 only
 bool fused_supported(int C, int H, int W, int iters, int ksize, int mode);
 template <typename T> int fused_forward(const FwdArgs<T>& a);
+size_t fused_workspace(int B, int C, int H, int W, int iters);   // optional scratch (0 = none)
 
 }  // namespace cspn

@@ -25,7 +25,10 @@
 #include <cuda.h>
 
 #include <cstddef>
+#include <atomic>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <type_traits>
 
 #include "cspn_common.cuh"
@@ -77,6 +80,15 @@ __device__ __forceinline__ u64 add2(u64 a, u64 b)
     u64 d;
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
+}
+// 1/s to within 1 ulp without the slow-path call of __frcp_rn: MUFU.RCP + one Newton step, branch free.
+// s = 0 gives inf and then NaN (0 * inf in the correction), so an all-zero weight sum still yields NaN weights.
+__device__ __forceinline__ float fast_rcp(float s)
+{
+    float r;
+    asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(s));
+    const float e = fmaf(-s, r, 1.f);
+    return fmaf(r, e, r);
 }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t cta_rank)
@@ -170,7 +182,29 @@ struct FusedParams {
     int stepx, stepy;     // origin spacing of cluster tiles
     int ew, eh;           // extent of one cluster tile
     int margin;           // decaying halo at cluster-tile edges that are not image borders (= iters)
+    uint4* inbox;         // GLB exchange only: one Inbox per CTA in global memory
+    uint32_t tag_base;    // GLB exchange only: tag of refresh e is tag_base + e
 };
+
+// Global-memory halo inbox of one CTA (GLB exchange), in uint4 units.  Every message is one 16-byte store
+// {lo, tag, hi, tag}: data and "valid" flag travel in the same transaction (the LL idea of collective libraries),
+// so the sender needs no fence and the receiver just re-reads the slot until both tags match.
+//   col[parity][side][TH]  then  row[parity][side][kHaloY][32]
+template <int TH> struct InboxGeom {
+    static constexpr uint32_t col_par = 2 * TH, col_side = TH;
+    static constexpr uint32_t row_base = 4 * TH, row_par = 2 * kHaloY * 32, row_side = kHaloY * 32;
+    static constexpr uint32_t size = 4 * TH + 4 * kHaloY * 32;
+};
+__device__ __forceinline__ void st_ll(uint4* slot, u64 v, uint32_t tag)
+{
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %2};" :: "l"(slot), "r"(__float_as_uint(lo_of(v))), "r"(tag), "r"(__float_as_uint(hi_of(v))) : "memory");
+}
+__device__ __forceinline__ uint4 ld_ll(const uint4* slot)
+{
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(slot) : "memory");
+    return v;
+}
 
 // Static part of one CTA's shared memory.  rowbuf: per-step edge rows of each warp (intra-CTA, one buffer
 // per step parity).  colbox/rowbox: the halo ring received from cluster neighbours, double buffered by
@@ -201,7 +235,7 @@ struct Stage {
     __host__ __device__ static int box_x(int ox) { const int v = ox - apron; return (v >= 0 ? v / align : -((-v + align - 1) / align)) * align; }
 };
 
-template <typename T, int P, int NW, int MODE, bool TMA>
+template <typename T, int P, int NW, int MODE, bool TMA, bool GLB>
 __global__ void __launch_bounds__(NW * 32, 1)
 fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant__ CUtensorMap gmap)
 {
@@ -247,7 +281,8 @@ fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant_
     TRACE(1);
     __syncthreads();
     // "my barriers exist": neighbours may only push into this CTA after everyone passed the matching wait
-    if (multi) cluster_arrive();
+    const bool hw_cluster = multi && !GLB;
+    if (hw_cluster) cluster_arrive();
 
     const T* db = p.depth + (size_t)plane * hw;
     const T* sb = p.sparse ? p.sparse + ((size_t)b * p.sparse_channels + (p.sparse_channels == 1 ? 0 : ch)) * hw : nullptr;
@@ -353,8 +388,8 @@ fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant_
             const bool row_in = gy >= 0 && gy < H;
             // n'_j = (1-m) * W_j / S.  S = 0 -> inf -> 0*inf = NaN like the reference's 0/0.  Pixels outside the
             // image are virtual: exactly zero weights and value (the reference's zero padding).
-            const float f0 = (row_in && x_in0) ? (1.f - lo_of(cc[i])) * __frcp_rn(lo_of(sum)) : 0.f;
-            const float f1 = (row_in && x_in1) ? (1.f - hi_of(cc[i])) * __frcp_rn(hi_of(sum)) : 0.f;
+            const float f0 = (row_in && x_in0) ? (1.f - lo_of(cc[i])) * fast_rcp(lo_of(sum)) : 0.f;
+            const float f1 = (row_in && x_in1) ? (1.f - hi_of(cc[i])) * fast_rcp(hi_of(sum)) : 0.f;
             scale[i] = pk(f0, f1);
         }
 #pragma unroll
@@ -378,7 +413,7 @@ fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant_
             float s0 = 0.f, s1 = 0.f;
 #pragma unroll
             for (int j = 0; j < 8; ++j) { w0[j] = expf(w0[j] - m0); w1[j] = expf(w1[j] - m1); s0 += w0[j]; s1 += w1[j]; }
-            const float f0 = in0 ? (1.f - lo_of(cc[i])) * __frcp_rn(s0) : 0.f, f1 = in1 ? (1.f - hi_of(cc[i])) * __frcp_rn(s1) : 0.f;
+            const float f0 = in0 ? (1.f - lo_of(cc[i])) * fast_rcp(s0) : 0.f, f1 = in1 ? (1.f - hi_of(cc[i])) * fast_rcp(s1) : 0.f;
             // taps that read the zero padding contribute n_j * 0 (no border renormalisation, pac.py:89): drop
             // their weight instead, so that whatever a tile-edge shuffle delivers for them is multiplied by 0
 #pragma unroll
@@ -396,7 +431,7 @@ fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant_
     const int lx0 = has_left ? 1 : 0, lx1 = has_right ? 30 : 31;
     const int ry0 = has_up ? kHaloY : 0, ry1 = has_down ? TH - 1 - kHaloY : TH - 1;
     const bool lane_auth = lane >= lx0 && lane <= lx1;
-    const uint32_t my_rank = multi ? cluster_ctarank() : 0;
+    const uint32_t my_rank = (uint32_t)(ccx + ccy * p.cx);      // == %cluster_ctarank for a (cx, cy, 1) cluster
     // bytes this CTA receives per refresh: 8 per row from the left / right neighbour, whole rows (all 32 lanes; halo
     // lanes of a row are overridden by the column boxes) from above / below, 2x8 from each diagonal neighbour
     const uint32_t expect_bytes = 8u * (uint32_t)(((has_left ? 1 : 0) + (has_right ? 1 : 0)) * (ry1 - ry0 + 1) +
@@ -405,12 +440,13 @@ fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant_
                                                             ((has_down && has_left) ? 1 : 0) + ((has_down && has_right) ? 1 : 0)));
     const uint32_t sm_base = smem_u32(&sm);
     using SmemT = Smem<NW, P>;
+    using IG = InboxGeom<TH>;
     constexpr uint32_t kColbox = offsetof(SmemT, colbox), kRowbox = offsetof(SmemT, rowbox), kHaloBar = offsetof(SmemT, halo_bar);
     constexpr uint32_t kColPar = sizeof(float) * 2 * TH * 2, kColSide = sizeof(float) * TH * 2;
     constexpr uint32_t kRowPar = sizeof(float) * 2 * kHaloY * kTileW, kRowSide = sizeof(float) * kHaloY * kTileW;
 
     TRACE(12);
-    if (multi) cluster_wait();
+    if (hw_cluster) cluster_wait();
     TRACE(13);
 
     // ---- T propagation steps ---------------------------------------------------------------------------
@@ -440,12 +476,18 @@ fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant_
         if (side == 0 && !has_left) side = -1;
         if (side == 1 && !has_right) side = -1;
         if (side >= 0) {
-            const uint32_t nb = mapa(sm_base, my_rank + dcy * p.cx + (side == 0 ? -1 : 1));
-            msg_dst = nb + kColbox + (side == 0 ? kColSide : 0u) + 8u * drow;          // my left rim lands in the neighbour's RIGHT box
-            msg_bar = nb + kHaloBar;
             msg_src = (uint32_t)(side * TH + srow) * 8u;
+            if (GLB) {
+                const uint32_t nblk = (blockIdx.z * gridDim.y + blockIdx.y + dcy) * gridDim.x + blockIdx.x + (side == 0 ? -1 : 1);
+                msg_dst = nblk * IG::size + (side == 0 ? IG::col_side : 0u) + (uint32_t)drow;   // uint4 index, parity 0; never 0
+            } else {
+                const uint32_t nb = mapa(sm_base, my_rank + dcy * p.cx + (side == 0 ? -1 : 1));
+                msg_dst = nb + kColbox + (side == 0 ? kColSide : 0u) + 8u * drow;      // my left rim lands in the neighbour's RIGHT box
+                msg_bar = nb + kHaloBar;
+            }
         }
     }
+    const uint32_t my_blk = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
 
     auto exchange_rows = [&](int par, u64& top, u64& bot) {
         // publish this warp's edge rows for the warps above / below (same CTA), fetch theirs
@@ -462,8 +504,9 @@ fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant_
     // r+1 (taps 0-2), r (taps 3,4) and r-1 (taps 5-7).  Three independent FMA chains are in flight, only one
     // row of shifted pairs is live, and output row r-1 completes exactly when old row r-1 is dead, so the
     // update is in place (no second copy of the strip).  PUSH: also send finished rim values to the neighbours.
-    auto compute_step = [&](auto push_tag, u64 top, u64 bot, int rpar) {
+    auto compute_step = [&](auto push_tag, u64 top, u64 bot, int rpar, uint32_t tag) {
         constexpr bool PUSH = decltype(push_tag)::value;
+        (void)tag;
         const uint32_t bar_off = kHaloBar + 8u * rpar;
         u64 acc[P];
 #pragma unroll
@@ -504,26 +547,40 @@ fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant_
             __syncwarp();
             if (msg_dst != 0u) {
                 const u64 v = *reinterpret_cast<const u64*>(reinterpret_cast<const unsigned char*>(&sm.colstage[rpar][0][0]) + msg_src);
-                st_async_b64(msg_dst + rpar * kColPar, v, msg_bar + 8u * rpar);
+                if (GLB) st_ll(p.inbox + msg_dst + rpar * IG::col_par, v, tag);
+                else st_async_b64(msg_dst + rpar * kColPar, v, msg_bar + 8u * rpar);
             }
             TRACE(91);
             if (has_up && warp == 0) {                                                   // warp-uniform
                 // my tile rows kHaloY .. 2*kHaloY-1 are the upper neighbour's bottom halo rows
-                const uint32_t d = mapa(sm_base, my_rank - p.cx);
+                if (GLB) {
+                    uint4* d = p.inbox + (size_t)(my_blk - gridDim.x) * IG::size + IG::row_base + rpar * IG::row_par + IG::row_side + lane;
 #pragma unroll
-                for (int h = 0; h < kHaloY; ++h)
-                    st_async_b64(d + kRowbox + rpar * kRowPar + kRowSide + 4u * (h * kTileW + 2 * lane), A[kHaloY + h], d + bar_off);
+                    for (int h = 0; h < kHaloY; ++h) st_ll(d + h * 32, A[kHaloY + h], tag);
+                } else {
+                    const uint32_t d = mapa(sm_base, my_rank - p.cx);
+#pragma unroll
+                    for (int h = 0; h < kHaloY; ++h)
+                        st_async_b64(d + kRowbox + rpar * kRowPar + kRowSide + 4u * (h * kTileW + 2 * lane), A[kHaloY + h], d + bar_off);
+                }
             }
             if (has_down && warp == NW - 1) {
-                const uint32_t d = mapa(sm_base, my_rank + p.cx);
+                if (GLB) {
+                    uint4* d = p.inbox + (size_t)(my_blk + gridDim.x) * IG::size + IG::row_base + rpar * IG::row_par + lane;
 #pragma unroll
-                for (int h = 0; h < kHaloY; ++h)
-                    st_async_b64(d + kRowbox + rpar * kRowPar + 4u * (h * kTileW + 2 * lane), A[P - 2 * kHaloY + h], d + bar_off);
+                    for (int h = 0; h < kHaloY; ++h) st_ll(d + h * 32, A[P - 2 * kHaloY + h], tag);
+                } else {
+                    const uint32_t d = mapa(sm_base, my_rank + p.cx);
+#pragma unroll
+                    for (int h = 0; h < kHaloY; ++h)
+                        st_async_b64(d + kRowbox + rpar * kRowPar + 4u * (h * kTileW + 2 * lane), A[P - 2 * kHaloY + h], d + bar_off);
+                }
             }
             TRACE(92);
         }
     };
 
+    bool poisoned = false;
     for (int t = 0; t < p.iters; t += 2) {
         // ===== even step t =====
         const int e = t / kPeriod, rpar = e & 1;
@@ -533,7 +590,34 @@ fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant_
         if (t < 24) TRACE(17 + 3 * t);
         if (multi && t > 0) {
             // take the refreshed halo ring (pushed by the neighbours during their step t-1)
-            mbar_wait(sm_base + kHaloBar + 8u * rpar, (uint32_t)(((e - 1) >> 1) & 1));
+            if (GLB) {
+                // poll this warp's slots of the global inbox until every tag is current, then drop the payload into
+                // the same shared-memory boxes the DSMEM path fills.  Lanes 0..P+1: left column rows ty0-1..ty0+P,
+                // lanes 16..16+P+1: right column; top / bottom warp: both halo rows, one slot per lane.
+                const uint32_t tag = p.tag_base + (uint32_t)e;
+                const uint4* box = p.inbox + (size_t)my_blk * IG::size;
+                const int sd = lane >> 4, row = warp * P - 1 + (lane & 15);
+                const bool want = (lane & 15) < P + 2 && row >= 0 && row < TH && (sd == 0 ? has_left : has_right);
+                const bool wr0 = has_up && warp == 0, wr1 = has_down && warp == NW - 1;
+                const uint4* cslot = box + rpar * IG::col_par + sd * IG::col_side + (want ? row : 0);
+                const uint4* rslot = box + IG::row_base + rpar * IG::row_par + (wr1 ? IG::row_side : 0u) + lane;
+                uint4 c = make_uint4(0, tag, 0, tag), r0 = c, r1 = c;
+                for (int spin = 0;; ++spin) {
+                    if (want) c = ld_ll(cslot);
+                    if (wr0 || wr1) { r0 = ld_ll(rslot); r1 = ld_ll(rslot + 32); }
+                    const bool ok = c.y == tag && c.w == tag && r0.y == tag && r0.w == tag && r1.y == tag && r1.w == tag;
+                    if (__all_sync(0xffffffffu, ok)) break;
+                    if (spin > (1 << 22)) { poisoned = true; break; }     // neighbours never showed up (grid not co-resident?): fail loudly, do not hang
+                }
+                if (want) *reinterpret_cast<uint2*>(&sm.colbox[rpar][sd][row][0]) = make_uint2(c.x, c.z);
+                if (wr0 || wr1) {
+                    *reinterpret_cast<uint2*>(&sm.rowbox[rpar][wr1 ? 1 : 0][0][2 * lane]) = make_uint2(r0.x, r0.z);
+                    *reinterpret_cast<uint2*>(&sm.rowbox[rpar][wr1 ? 1 : 0][1][2 * lane]) = make_uint2(r1.x, r1.z);
+                }
+                __syncwarp();
+            } else {
+                mbar_wait(sm_base + kHaloBar + 8u * rpar, (uint32_t)(((e - 1) >> 1) & 1));
+            }
             if (has_up && warp == 0) {
 #pragma unroll
                 for (int h = 0; h < kHaloY; ++h) A[h] = *reinterpret_cast<const u64*>(&sm.rowbox[rpar][0][h][2 * lane]);
@@ -553,7 +637,7 @@ fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant_
             }
         }
         if (t < 24) TRACE(18 + 3 * t);
-        compute_step(std::false_type{}, top, bot, 0);
+        compute_step(std::false_type{}, top, bot, 0, 0u);
         if (t + 1 >= p.iters) break;
         // ===== odd step t+1: its results feed the refresh at step t+2 =====
         if (t < 23) TRACE(16 + 3 * (t + 1));
@@ -561,21 +645,31 @@ fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant_
         if (t < 23) { TRACE(17 + 3 * (t + 1)); TRACE(18 + 3 * (t + 1)); }
         if (multi && t + 2 < p.iters) {
             const int rnext = (e + 1) & 1;
-            if (threadIdx.x == 0) mbar_arrive_expect_tx(sm_base + kHaloBar + 8u * rnext, expect_bytes);
+            if (!GLB && threadIdx.x == 0) mbar_arrive_expect_tx(sm_base + kHaloBar + 8u * rnext, expect_bytes);
             TRACE(89);
-            compute_step(std::true_type{}, top, bot, rnext);
+            compute_step(std::true_type{}, top, bot, rnext, p.tag_base + (uint32_t)(e + 1));
         } else {
-            compute_step(std::false_type{}, top, bot, 0);
+            compute_step(std::false_type{}, top, bot, 0, 0u);
         }
     }
 
     TRACE(14);
+    if (GLB && multi) {
+        // every message addressed to this CTA has been consumed: leave the inbox clean for the next launch / graph replay
+        __syncthreads();
+        uint4* box = p.inbox + (size_t)my_blk * IG::size;
+        for (uint32_t i = threadIdx.x; i < IG::size; i += NW * 32) box[i] = make_uint4(0, 0, 0, 0);
+    }
     // ---- epilogue: only the final depth goes back to HBM, and only from the pixels this CTA is authoritative for
     const int vx0 = tix > 0 ? tix * p.stepx + p.margin : 0;
     const int vx1 = tix == p.ntx - 1 ? W : tix * p.stepx + p.ew - p.margin;
     const int vy0 = tiy > 0 ? tiy * p.stepy + p.margin : 0;
     const int vy1 = tiy == p.nty - 1 ? H : tiy * p.stepy + p.eh - p.margin;
     T* ob = p.out + (size_t)plane * hw;
+    if (poisoned) {
+#pragma unroll
+        for (int i = 0; i < P; ++i) A[i] = pk(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000));
+    }
     if (lane_auth) {
         const bool ok0 = gx >= vx0 && gx < vx1 && gx < W, ok1 = gx + 1 >= vx0 && gx + 1 < vx1 && gx + 1 < W;
 #pragma unroll
@@ -662,10 +756,29 @@ bool make_guidance_map(const FwdArgs<T>& a, CUtensorMap* map)
     return r == CUDA_SUCCESS;
 }
 
-template <typename T, int MODE, bool TMA>
+constexpr size_t kInboxBytes = (size_t)InboxGeom<kTH>::size * sizeof(uint4);
+constexpr long kMaxGlobalExchangeCtas = 512;      // upper bound used for the workspace query (device independent)
+
+// Per-device facts needed to choose the exchange transport, queried once.
+struct DeviceFacts { bool valid; int sms; int max_clusters[17]; };
+DeviceFacts& device_facts(int dev)
+{
+    static DeviceFacts facts[64];
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    DeviceFacts& f = facts[dev & 63];
+    if (!f.valid) {
+        cudaDeviceGetAttribute(&f.sms, cudaDevAttrMultiProcessorCount, dev);
+        for (int i = 0; i <= 16; ++i) f.max_clusters[i] = -1;
+        f.valid = true;
+    }
+    return f;
+}
+
+template <typename T, int MODE, bool TMA, bool GLB>
 int launch_variant(const FusedParams<T>& p, const CUtensorMap& map, const Tiling& tl, int planes, cudaStream_t stream)
 {
-    auto kern = fused3x3_kernel<T, kP, kNW, MODE, TMA>;
+    auto kern = fused3x3_kernel<T, kP, kNW, MODE, TMA, GLB>;
     const size_t smem = sizeof(Smem<kNW, kP>) + (TMA ? Stage<T, kTH, MODE>::bytes : 0);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -676,14 +789,46 @@ int launch_variant(const FusedParams<T>& p, const CUtensorMap& map, const Tiling
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = (unsigned)tl.cx; at[0].val.clusterDim.y = (unsigned)tl.cy; at[0].val.clusterDim.z = 1;
+    if (GLB) {
+        // neighbours talk through global memory and spin on it: every CTA of the grid must be resident
+        at[0].id = cudaLaunchAttributeCooperative;
+        at[0].val.cooperative = 1;
+    } else {
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)tl.cx; at[0].val.clusterDim.y = (unsigned)tl.cy; at[0].val.clusterDim.z = 1;
+    }
     cfg.attrs = at; cfg.numAttrs = 1;
     e = cudaLaunchKernelEx(&cfg, kern, p, map);
     if (e != cudaSuccess) return (int)e;
     ++call_stats().launches;
     return 0;
 }
+
+// How many clusters of this shape can be resident at once (1 CTA per SM kernel): decides whether the cluster
+// path would need more than one wave.
+template <typename T, int MODE>
+int max_active_clusters(int dev, const Tiling& tl)
+{
+    DeviceFacts& f = device_facts(dev);
+    const int size = tl.cx * tl.cy;
+    if (f.max_clusters[size] >= 0) return f.max_clusters[size];
+    auto kern = fused3x3_kernel<T, kP, kNW, MODE, true, false>;
+    const size_t smem = sizeof(Smem<kNW, kP>) + Stage<T, kTH, MODE>::bytes;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)tl.cx, (unsigned)tl.cy, 64); cfg.blockDim = dim3(kNW * 32); cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)tl.cx; at[0].val.clusterDim.y = (unsigned)tl.cy; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); n = 1 << 20; }
+    f.max_clusters[size] = n;
+    return n;
+}
+
+std::atomic<uint32_t> g_epoch{0x5a17u};
 
 template <typename T, int MODE>
 int launch(const FwdArgs<T>& a, const Tiling& tl)
@@ -693,10 +838,27 @@ int launch(const FwdArgs<T>& a, const Tiling& tl)
     p.C = a.C; p.H = a.H; p.W = a.W; p.iters = a.iters;
     p.cx = tl.cx; p.cy = tl.cy; p.ntx = tl.ntx; p.nty = tl.nty; p.stepx = tl.stepx; p.stepy = tl.stepy; p.ew = tl.ew; p.eh = tl.eh;
     p.margin = a.iters;
+    const int planes = a.B * a.C;
+    // Exchange transport: DSMEM inside hardware clusters by default.  When the clusters would not all be resident
+    // at once (e.g. 8 NYU images = 8 clusters of 15 CTAs but the GPU places only 7) while the whole grid of CTAs
+    // would, drop the clusters and exchange through global memory instead: one wave instead of two.
+    bool glb = false;
+    const long ctas = tl.ctas * planes;
+    static const int force = [] { const char* v = getenv("CSPN_EXCHANGE"); return !v ? 0 : (!strcmp(v, "dsmem") ? 1 : (!strcmp(v, "global") ? 2 : 0)); }();   // debugging knob
+    if (force != 1 && tl.cx * tl.cy > 1 && a.ws && a.ws_bytes >= (size_t)ctas * kInboxBytes && ctas <= kMaxGlobalExchangeCtas && a.iters <= 120) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (ctas <= device_facts(dev).sms && (force == 2 || (long)tl.ntx * tl.nty * planes > max_active_clusters<T, MODE>(dev, tl))) glb = true;
+    }
+    if (glb) {
+        p.inbox = (uint4*)a.ws;
+        p.tag_base = g_epoch.fetch_add(1, std::memory_order_relaxed) << 7;      // + refresh index (1..60) is never 0
+    }
     alignas(64) CUtensorMap map;
     memset(&map, 0, sizeof map);
-    if (make_guidance_map<T, MODE>(a, &map)) return launch_variant<T, MODE, true>(p, map, tl, a.B * a.C, a.stream);
-    return launch_variant<T, MODE, false>(p, map, tl, a.B * a.C, a.stream);   // unaligned guidance: plain-load prologue
+    const bool tma = make_guidance_map<T, MODE>(a, &map);                        // false: unaligned guidance, plain-load prologue
+    if (glb) return tma ? launch_variant<T, MODE, true, true>(p, map, tl, planes, a.stream) : launch_variant<T, MODE, false, true>(p, map, tl, planes, a.stream);
+    return tma ? launch_variant<T, MODE, true, false>(p, map, tl, planes, a.stream) : launch_variant<T, MODE, false, false>(p, map, tl, planes, a.stream);
 }
 
 }  // namespace
@@ -715,6 +877,14 @@ bool fused_supported(int C, int H, int W, int iters, int ksize, int mode)
     if (ksize != 3 || iters < 1) return false;
     if ((long)H * W > (1l << 30)) return false;
     return choose_tiling(H, W, iters).ok;
+}
+
+size_t fused_workspace(int B, int C, int H, int W, int iters)
+{
+    const Tiling tl = choose_tiling(H, W, iters);
+    if (!tl.ok || tl.cx * tl.cy == 1) return 0;
+    const long ctas = tl.ctas * (long)B * C;
+    return ctas <= kMaxGlobalExchangeCtas ? (size_t)ctas * kInboxBytes : 0;     // inboxes of the global-memory exchange
 }
 
 template <typename T>
