@@ -45,6 +45,14 @@ bool use_fused(int C, int H, int W, int iters, int ksize, int mode, int* err)
     return path != CSPN_PATH_GENERIC && ok;
 }
 
+bool use_fused_bwd(int C, int H, int W, int iters, int ksize, int mode, int* err)
+{
+    const int path = g_path.load(std::memory_order_relaxed);
+    const bool ok = fused_bwd_supported(C, H, W, iters, ksize, mode);
+    if (path == CSPN_PATH_FUSED && !ok && err) *err = CSPN_ERR_BAD_KERNEL_SIZE;
+    return path != CSPN_PATH_GENERIC && ok;
+}
+
 template <typename T>
 int forward_impl(const T* guidance, int64_t gbs, const T* depth, const T* sparse, int sparse_channels, T* out,
                  int B, int C, int H, int W, int iters, int ksize, int mode, void* ws, size_t ws_bytes, void* stream)
@@ -85,13 +93,20 @@ int backward_impl(const T* grad_out, const T* guidance, int64_t gbs, int Cg, con
     if (rc != CSPN_OK || B == 0) return rc;
     if (!grad_out || !grad_guidance || !grad_depth) return CSPN_ERR_NULL_POINTER;
     if (Cg < tt.n) return CSPN_ERR_BAD_STRIDE;
+    BwdArgs<T> a{grad_out, guidance, gbs, Cg, depth, sparse, sparse ? sparse_channels : 1, grad_guidance, grad_depth,
+                 B, C, H, W, iters, ksize, mode, ws, ws_bytes, (cudaStream_t)stream};
+    call_stats().launches = 0;
+    int err = CSPN_OK;
+    if (iters > 0 && use_fused_bwd(C, H, W, iters, ksize, mode, &err)) {
+        rc = fused_backward<T>(a);
+        if (rc == CSPN_OK) call_stats().path = CSPN_PATH_FUSED;
+        return rc;
+    }
+    if (err != CSPN_OK) return err;
     if (iters > 0) {
         const size_t need = generic_bwd_workspace(B, C, H, W, iters, tt.n);
         if (!ws || ws_bytes < need) return CSPN_ERR_WORKSPACE;
     }
-    BwdArgs<T> a{grad_out, guidance, gbs, Cg, depth, sparse, sparse ? sparse_channels : 1, grad_guidance, grad_depth,
-                 B, C, H, W, iters, ksize, mode, ws, ws_bytes, (cudaStream_t)stream};
-    call_stats().launches = 0;
     rc = generic_backward<T>(a, tt);
     if (rc == CSPN_OK) call_stats().path = CSPN_PATH_GENERIC;
     return rc;
@@ -186,6 +201,7 @@ size_t cspn_bwd_workspace_bytes(int B, int C, int H, int W, int iters, int ksize
 {
     TapTable tt;
     if (!make_taps(mode, ksize, &tt) || B < 1 || C < 1 || H < 1 || W < 1 || iters < 1) return 0;
+    if (use_fused_bwd(C, H, W, iters, ksize, mode, nullptr)) return fused_bwd_workspace(B, C, H, W, iters);
     return generic_bwd_workspace(B, C, H, W, iters, tt.n);
 }
 

@@ -85,4 +85,9 @@ bool fused_supported(int C, int H, int W, int iters, int ksize, int mode);
 template <typename T> int fused_forward(const FwdArgs<T>& a);
 size_t fused_workspace(int B, int C, int H, int W, int iters);   // optional scratch (0 = none)
 
+// fused backward (cspn_fused3x3_bwd.cu): recompute + reverse sweep + Jacobians in one launch, 3x3, one depth channel
+bool fused_bwd_supported(int C, int H, int W, int iters, int ksize, int mode);
+template <typename T> int fused_backward(const BwdArgs<T>& a);
+size_t fused_bwd_workspace(int B, int C, int H, int W, int iters);
+
 }  // namespace cspn

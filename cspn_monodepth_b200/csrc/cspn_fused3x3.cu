@@ -1,867 +1,7 @@
-// Fused CSPN forward for 3x3 neighbourhoods (both reference modes): the whole T-step recurrence in ONE
-// launch.  Replaces the loops at CSPN_new.py:80-90 and CSPN_ours.py:47-53 (pac.py:89-94 per step).
-//
-// Design (B200, sm_100a) - see DESIGN.md section 3 for the derivation and the measured numbers behind it:
-//  * The recurrence is FMA-bound once fused (8 FMA per pixel per step against 44 B of HBM traffic per
-//    pixel in total), and only the register file can feed the FMA pipe: the 8 loop-invariant, pre-
-//    normalised weights of every pixel plus the re-injection term stay in REGISTERS for all T steps
-//    (the reference recomputes the normalisation every step).  A thread owns a 2-wide x P-tall strip of
-//    pixels as packed f32x2 pairs so the inner loop is 8 FFMA2 per pixel pair (fma.rn.f32x2: two FMAs per
-//    issue slot - leaves issue slots for the data movement).
-//  * Left/right neighbours come from warp shuffles, rows above/below from the thread's own registers;
-//    warps of a CTA exchange their edge rows through shared memory once per step.
-//  * A register-resident CTA tile is only 64 x (NW*P) pixels, far smaller than the T-pixel dependency cone,
-//    so CTAs cooperate as a thread-block CLUSTER (up to 16 CTAs, e.g. 5x3 = one whole 304x228 NYU image):
-//    every second step each CTA pushes a 2-pixel-deep halo ring straight into its 8 neighbours' shared
-//    memory with st.async (DSMEM) and the neighbour's mbarrier counts the bytes - no cluster-wide barrier,
-//    no fence.  Only at the edge of a cluster tile that is not an image border does the classic shrinking
-//    (trapezoid) halo of T pixels apply.
-//  * The guidance tile (8 channels, 1-pixel apron) is staged once into shared memory by TMA
-//    (cp.async.bulk.tensor, one box per channel, out-of-image elements zero-filled by the hardware = the
-//    reference's ZeroPad2d), weights are normalised from there into registers; depth/sparse come in with
-//    plain coalesced loads that overlap the TMA.
-//  * HBM traffic is the algorithmic minimum: guidance/depth/sparse are read once (plus halo overlap that
-//    L2 serves), only the final depth is written.
-#include <cuda.h>
-
-#include <cstddef>
-#include <atomic>
-#include <cstdlib>
-#include <cstring>
-#include <mutex>
-#include <type_traits>
-
-#include "cspn_common.cuh"
+// Forward instantiations and host entry points of the fused 3x3 CSPN kernel (cspn_fused3x3.cuh).
+#include "cspn_fused3x3.cuh"
 
 namespace cspn {
-namespace {
-
-typedef unsigned long long u64;
-
-constexpr int kTileW = 64;            // 32 lanes x 2 pixels
-constexpr int kHaloX = 2;             // one lane (= one pixel pair) of halo per side between CTAs of a cluster
-constexpr int kHaloY = 2;             // two rows of halo per side between CTAs of a cluster
-constexpr int kPeriod = 2;            // halo refresh period in steps (= halo depth)
-constexpr int kStepX = kTileW - 2 * kHaloX;   // x spacing of CTA tiles inside a cluster (60)
-
-// ---- small PTX wrappers ------------------------------------------------------------------------------
-__device__ __forceinline__ u64 pk(float lo, float hi)
-{
-    u64 d;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
-    return d;
-}
-__device__ __forceinline__ float lo_of(u64 v)
-{
-    float lo, hi;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-    return lo;
-}
-__device__ __forceinline__ float hi_of(u64 v)
-{
-    float lo, hi;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-    return hi;
-}
-__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c)
-{
-    u64 d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-__device__ __forceinline__ u64 mul2(u64 a, u64 b)
-{
-    u64 d;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-__device__ __forceinline__ u64 add2(u64 a, u64 b)
-{
-    u64 d;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-// 1/s to within 1 ulp without the slow-path call of __frcp_rn: MUFU.RCP + one Newton step, branch free.
-// s = 0 gives inf and then NaN (0 * inf in the correction), so an all-zero weight sum still yields NaN weights.
-__device__ __forceinline__ float fast_rcp(float s)
-{
-    float r;
-    asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(s));
-    const float e = fmaf(-s, r, 1.f);
-    return fmaf(r, e, r);
-}
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t cta_rank)
-{
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta_rank));
-    return r;
-}
-// 8-byte store into another CTA's shared memory; the bytes are counted on that CTA's mbarrier.
-__device__ __forceinline__ void st_async_b64(uint32_t remote_addr, u64 v, uint32_t remote_bar)
-{
-    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
-                 :: "r"(remote_addr), "l"(v), "r"(remote_bar) : "memory");
-}
-// Same, predicated: lanes with pred == false issue nothing (no divergent branch around the store).
-__device__ __forceinline__ void st_async_b64_if(bool pred, uint32_t remote_addr, u64 v, uint32_t remote_bar)
-{
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t"
-                 "@q st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];\n\t}"
-                 :: "r"(remote_addr), "l"(v), "r"(remote_bar), "r"((uint32_t)pred) : "memory");
-}
-// Bulk copy of `bytes` (multiple of 16) from this CTA's shared memory into a cluster neighbour's, counted on the
-// neighbour's mbarrier.  Runs on the async copy engine; the issuing thread does not wait.
-__device__ __forceinline__ void bulk_s2s(uint32_t remote_dst, uint32_t local_src, uint32_t bytes, uint32_t remote_bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(remote_dst), "r"(local_src), "r"(bytes), "r"(remote_bar) : "memory");
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
-}
-// Default (cta-scope acquire) semantics: in both uses the awaited bytes land in THIS CTA's shared memory and
-// are published by the barrier's complete_tx (TMA box / neighbours' st.async), like any TMA consumer.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@!p bra WAIT_%=;\n\t}"
-        :: "r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3)
-{
-    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-                 :: "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
-}
-// relaxed: the only thing published before it is mbarrier initialisation, which fence.mbarrier_init covers
-__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
-__device__ __forceinline__ float2 to_f32x2(float2 v) { return v; }
-__device__ __forceinline__ float2 to_f32x2(__half2 v) { return __half22float2(v); }
-__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-__device__ __forceinline__ uint32_t cluster_ctarank()
-{
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-
-// (x-1,x) and (x+1,x+2) pairs of a row from its (x,x+1) pair: one shuffle + one register move each.
-__device__ __forceinline__ void shifted(u64 a, u64& s1, u64& s2)
-{
-    const float lo = lo_of(a), hi = hi_of(a);
-    const float l = __shfl_up_sync(0xffffffffu, hi, 1), r = __shfl_down_sync(0xffffffffu, lo, 1);
-    s1 = pk(l, lo);
-    s2 = pk(hi, r);
-}
-
-// Optional cycle trace (build with -DCSPN_TRACE): lane 0 of every warp stamps clock64() at fixed points.
-#ifdef CSPN_TRACE
-__device__ long long* g_trace = nullptr;
-constexpr int kTraceSlots = 96;
-#define TRACE(slot) do { if (g_trace && (threadIdx.x & 31) == 0) g_trace[((size_t)(blockIdx.z * gridDim.y * gridDim.x + blockIdx.y * gridDim.x + blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kTraceSlots + (slot)] = clock64(); } while (0)
-#else
-#define TRACE(slot) do { } while (0)
-#endif
-
-template <typename T>
-struct FusedParams {
-    const T* g; int64_t gbs;
-    const T* depth; const T* sparse; int sparse_channels;
-    T* out;
-    int C, H, W, iters;
-    int cx, cy;           // cluster dims (CTAs)
-    int ntx, nty;         // cluster tiles per image
-    int stepx, stepy;     // origin spacing of cluster tiles
-    int ew, eh;           // extent of one cluster tile
-    int margin;           // decaying halo at cluster-tile edges that are not image borders (= iters)
-    uint4* inbox;         // GLB exchange only: one Inbox per CTA in global memory
-    uint32_t tag_base;    // GLB exchange only: tag of refresh e is tag_base + e
-};
-
-// Global-memory halo inbox of one CTA (GLB exchange), in uint4 units.  Every message is one 16-byte store
-// {lo, tag, hi, tag}: data and "valid" flag travel in the same transaction (the LL idea of collective libraries),
-// so the sender needs no fence and the receiver just re-reads the slot until both tags match.
-//   col[parity][side][TH]  then  row[parity][side][kHaloY][32]
-template <int TH> struct InboxGeom {
-    static constexpr uint32_t col_par = 2 * TH, col_side = TH;
-    static constexpr uint32_t row_base = 4 * TH, row_par = 2 * kHaloY * 32, row_side = kHaloY * 32;
-    static constexpr uint32_t size = 4 * TH + 4 * kHaloY * 32;
-};
-__device__ __forceinline__ void st_ll(uint4* slot, u64 v, uint32_t tag)
-{
-    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %2};" :: "l"(slot), "r"(__float_as_uint(lo_of(v))), "r"(tag), "r"(__float_as_uint(hi_of(v))) : "memory");
-}
-__device__ __forceinline__ uint4 ld_ll(const uint4* slot)
-{
-    uint4 v;
-    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(slot) : "memory");
-    return v;
-}
-
-// Static part of one CTA's shared memory.  rowbuf: per-step edge rows of each warp (intra-CTA, one buffer
-// per step parity).  colbox/rowbox: the halo ring received from cluster neighbours, double buffered by
-// refresh parity, each with its own transaction-counting mbarrier.
-template <int NW, int P>
-struct __align__(128) Smem {
-    float rowbuf[2][NW][2][kTileW];
-    float colbox[2][2][NW * P][2];        // [parity][side: 0 left, 1 right][tile row][2 px]
-    float rowbox[2][2][kHaloY][kTileW];   // [parity][side: 0 top, 1 bottom][halo row][tile x]
-    u64 colstage[2][2][NW * P];           // [parity][side][tile row]: rim columns on their way to the left / right neighbour
-    u64 halo_bar[2];
-    u64 tma_bar[8];
-};
-
-// Geometry of the TMA staging buffer for the guidance tile.  The innermost start coordinate of a TMA box must
-// be 16-byte aligned in global memory (measured: anything else traps as an illegal instruction), so the box
-// starts at the aligned column at or left of (tile x - apron) and is wide enough for every sub-offset.
-template <typename T, int TH, int MODE>
-struct Stage {
-    static constexpr int apron = MODE == CSPN_MODE_NEW ? 1 : 0;       // mode NEW gathers weights from the 8 neighbours
-    static constexpr int rows = TH + 2 * apron;
-    static constexpr int align = 16 / (int)sizeof(T);                // elements per 16 bytes
-    static constexpr int cols = ((kTileW + 2 * apron + align - 1 + align - 1) / align) * align;   // fp32: 72 | 68, fp16: 80 | 72
-    static constexpr int box_bytes = rows * cols * (int)sizeof(T);   // what one TMA box delivers
-    static constexpr int plane = ((box_bytes + 127) / 128) * 128 / (int)sizeof(T);   // elements per channel, 128-byte aligned for TMA
-    static constexpr size_t bytes = (size_t)8 * plane * sizeof(T);
-    // aligned box start for a tile whose first pixel column is ox (floor division, ox - apron may be negative)
-    __host__ __device__ static int box_x(int ox) { const int v = ox - apron; return (v >= 0 ? v / align : -((-v + align - 1) / align)) * align; }
-};
-
-template <typename T, int P, int NW, int MODE, bool TMA, bool GLB>
-__global__ void __launch_bounds__(NW * 32, 1)
-fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant__ CUtensorMap gmap)
-{
-    constexpr int TH = NW * P;
-    constexpr int STEPY = TH - 2 * kHaloY;
-    using St = Stage<T, TH, MODE>;
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    Smem<NW, P>& sm = *reinterpret_cast<Smem<NW, P>*>(smem_raw);
-    const T* stage = reinterpret_cast<const T*>(smem_raw + sizeof(Smem<NW, P>));
-
-    TRACE(0);
-    const bool multi = p.cx * p.cy > 1;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int ccx = blockIdx.x % p.cx, ccy = blockIdx.y % p.cy;
-    const int tix = blockIdx.x / p.cx, tiy = blockIdx.y / p.cy;
-    const int plane = blockIdx.z, b = plane / p.C, ch = plane - b * p.C;
-    const bool has_left = ccx > 0, has_right = ccx < p.cx - 1, has_up = ccy > 0, has_down = ccy < p.cy - 1;
-    const int H = p.H, W = p.W;
-    const size_t hw = (size_t)H * W;
-
-    // image coordinates of this CTA tile / this thread's strip: columns gx, gx+1, rows gy0 .. gy0+P-1
-    const int ox = tix * p.stepx + ccx * kStepX, oy = tiy * p.stepy + ccy * STEPY;
-    const int gx = ox + 2 * lane;
-    const int gy0 = oy + warp * P;
-
-    // ---- barriers + TMA issue (one thread) --------------------------------------------------------------
-    if (threadIdx.x == 0) {
-        mbar_init(smem_u32(&sm.halo_bar[0]), 1);
-        mbar_init(smem_u32(&sm.halo_bar[1]), 1);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) mbar_init(smem_u32(&sm.tma_bar[k]), 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if (TMA) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const uint32_t bar = smem_u32(&sm.tma_bar[k]);
-                mbar_arrive_expect_tx(bar, (uint32_t)St::box_bytes);
-                tma_load_4d(smem_u32(stage + (size_t)k * St::plane), &gmap, bar, St::box_x(ox), oy - St::apron, k, b);
-            }
-        }
-    }
-    TRACE(1);
-    __syncthreads();
-    // "my barriers exist": neighbours may only push into this CTA after everyone passed the matching wait
-    const bool hw_cluster = multi && !GLB;
-    if (hw_cluster) cluster_arrive();
-
-    const T* db = p.depth + (size_t)plane * hw;
-    const T* sb = p.sparse ? p.sparse + ((size_t)b * p.sparse_channels + (p.sparse_channels == 1 ? 0 : ch)) * hw : nullptr;
-
-    // ---- prologue: loop-invariant weights n'_j = (1-m) * n_j, re-injection c = m*d0, r^0 = d0 -------------
-    // internal tap order j: (dy,dx) row-major without the centre; mode NEW channel k = 7 - j reads the
-    // guidance AT THE NEIGHBOUR p + o (CSPN_new.py:43-67), mode OURS channel j reads it at p (CSPN_ours.py:37-41).
-    u64 nw[P][8], cc[P], A[P];
-    const bool x_in0 = gx >= 0 && gx < W, x_in1 = gx + 1 >= 0 && gx + 1 < W;
-    const bool vec_ok = (W & 1) == 0;        // pairs start at even x: 8-byte (fp32) / 4-byte (fp16) aligned when W is even
-
-    // depth and sparse first: plain coalesced loads, all issued back to back (clamped addresses, no branches
-    // between them) so that they are in flight together while the TMA boxes land
-    if (vec_ok) {
-        typedef typename std::conditional<sizeof(T) == 4, float2, __half2>::type V2;
-        const int cgx = min(max(gx, 0), W - 2);
-        V2 dv[P], sv[P];
-#pragma unroll
-        for (int i = 0; i < P; ++i) {
-            const size_t off = (size_t)min(max(gy0 + i, 0), H - 1) * W + cgx;
-            dv[i] = *reinterpret_cast<const V2*>(db + off);
-            if (sb) sv[i] = *reinterpret_cast<const V2*>(sb + off);
-        }
-#pragma unroll
-        for (int i = 0; i < P; ++i) {
-            const int gy = gy0 + i;
-            const bool in = gy >= 0 && gy < H && x_in0;        // W even and gx even: both pixels of the pair are in or out together
-            const float2 d = to_f32x2(dv[i]);
-            float2 m = make_float2(0.f, 0.f);
-            if (sb) { const float2 sp2 = to_f32x2(sv[i]); m = make_float2(signf(sp2.x), signf(sp2.y)); }
-            A[i] = in ? pk(d.x, d.y) : 0ull;
-            cc[i] = in ? pk(m.x, m.y) : 0ull;               // holds the mask until the weights are folded below
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < P; ++i) {
-            const int gy = gy0 + i;
-            const bool row_in = gy >= 0 && gy < H;
-            float d0 = 0.f, d1 = 0.f, m0 = 0.f, m1 = 0.f;
-            const size_t off = (size_t)gy * W + gx;
-            if (row_in && x_in0) { d0 = to_f32(db[off]); if (sb) m0 = signf(to_f32(sb[off])); }
-            if (row_in && x_in1) { d1 = to_f32(db[off + 1]); if (sb) m1 = signf(to_f32(sb[off + 1])); }
-            A[i] = pk(d0, d1);
-            cc[i] = pk(m0, m1);
-        }
-    }
-
-    TRACE(2);
-    // raw guidance values -> registers
-    if (TMA) {
-        const int x_off = ox - St::box_x(ox);           // column of the tile's first pixel inside the staged box
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            mbar_wait(smem_u32(&sm.tma_bar[k]), 0);
-            TRACE(3 + k);
-            const T* sp = stage + (size_t)k * St::plane;
-            if (MODE == CSPN_MODE_NEW) {
-                const int j = 7 - k, jj = j < 4 ? j : j + 1;
-                const int dy = jj / 3 - 1, dx = jj % 3 - 1;
-#pragma unroll
-                for (int i = 0; i < P; ++i) {
-                    const T* src = sp + (warp * P + i + 1 + dy) * St::cols + x_off + 2 * lane + dx;
-                    nw[i][j] = pk(fabsf(to_f32(src[0])), fabsf(to_f32(src[1])));      // zero-filled outside the image
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < P; ++i) {
-                    const T* src = sp + (warp * P + i) * St::cols + x_off + 2 * lane;
-                    nw[i][k] = pk(to_f32(src[0]), to_f32(src[1]));
-                }
-            }
-        }
-    } else {
-        const T* gb = p.g + (size_t)b * p.gbs;
-#pragma unroll
-        for (int i = 0; i < P; ++i) {
-            const int gy = gy0 + i;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int jj = j < 4 ? j : j + 1;
-                const int dy = MODE == CSPN_MODE_NEW ? jj / 3 - 1 : 0, dx = MODE == CSPN_MODE_NEW ? jj % 3 - 1 : 0;
-                const int k = MODE == CSPN_MODE_NEW ? 7 - j : j, yy = gy + dy, xx = gx + dx;
-                const bool rin = yy >= 0 && yy < H;
-                const T* src = gb + (size_t)k * hw + (size_t)yy * W + xx;
-                float v0 = (rin && xx >= 0 && xx < W) ? to_f32(src[0]) : 0.f;
-                float v1 = (rin && xx + 1 >= 0 && xx + 1 < W) ? to_f32(src[1]) : 0.f;
-                if (MODE == CSPN_MODE_NEW) { v0 = fabsf(v0); v1 = fabsf(v1); }
-                nw[i][j] = pk(v0, v1);
-            }
-        }
-    }
-
-    TRACE(11);
-    // normalise, fold the sparse mask in (packed f32x2 arithmetic, all rows' reductions independent)
-    if (MODE == CSPN_MODE_NEW) {
-        u64 scale[P];
-#pragma unroll
-        for (int i = 0; i < P; ++i) {
-            u64 sum = nw[i][7];                                       // reference order k = 0..7 (CSPN_new.py:124), k = 7 - j
-#pragma unroll
-            for (int k = 1; k < 8; ++k) sum = add2(sum, nw[i][7 - k]);
-            const int gy = gy0 + i;
-            const bool row_in = gy >= 0 && gy < H;
-            // n'_j = (1-m) * W_j / S.  S = 0 -> inf -> 0*inf = NaN like the reference's 0/0.  Pixels outside the
-            // image are virtual: exactly zero weights and value (the reference's zero padding).
-            const float f0 = (row_in && x_in0) ? (1.f - lo_of(cc[i])) * fast_rcp(lo_of(sum)) : 0.f;
-            const float f1 = (row_in && x_in1) ? (1.f - hi_of(cc[i])) * fast_rcp(hi_of(sum)) : 0.f;
-            scale[i] = pk(f0, f1);
-        }
-#pragma unroll
-        for (int i = 0; i < P; ++i) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) nw[i][j] = mul2(nw[i][j], scale[i]);
-            cc[i] = mul2(cc[i], A[i]);                                // c = m * d0
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < P; ++i) {
-            const int gy = gy0 + i;
-            const bool row_in = gy >= 0 && gy < H;
-            const bool in0 = row_in && x_in0, in1 = row_in && x_in1;
-            float w0[8], w1[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { w0[j] = lo_of(nw[i][j]); w1[j] = hi_of(nw[i][j]); }
-            float m0 = w0[0], m1 = w1[0];
-#pragma unroll
-            for (int j = 1; j < 8; ++j) { m0 = fmaxf(m0, w0[j]); m1 = fmaxf(m1, w1[j]); }
-            float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { w0[j] = expf(w0[j] - m0); w1[j] = expf(w1[j] - m1); s0 += w0[j]; s1 += w1[j]; }
-            const float f0 = in0 ? (1.f - lo_of(cc[i])) * fast_rcp(s0) : 0.f, f1 = in1 ? (1.f - hi_of(cc[i])) * fast_rcp(s1) : 0.f;
-            // taps that read the zero padding contribute n_j * 0 (no border renormalisation, pac.py:89): drop
-            // their weight instead, so that whatever a tile-edge shuffle delivers for them is multiplied by 0
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int jj = j < 4 ? j : j + 1;
-                const int yy = gy + jj / 3 - 1, xx = gx + jj % 3 - 1;
-                const bool rin = yy >= 0 && yy < H;
-                nw[i][j] = pk((rin && xx >= 0 && xx < W) ? w0[j] * f0 : 0.f, (rin && xx + 1 >= 0 && xx + 1 < W) ? w1[j] * f1 : 0.f);
-            }
-            cc[i] = mul2(cc[i], A[i]);
-        }
-    }
-
-    // which lanes / rows of this CTA tile are authoritative (not halo owned by a cluster neighbour)
-    const int lx0 = has_left ? 1 : 0, lx1 = has_right ? 30 : 31;
-    const int ry0 = has_up ? kHaloY : 0, ry1 = has_down ? TH - 1 - kHaloY : TH - 1;
-    const bool lane_auth = lane >= lx0 && lane <= lx1;
-    const uint32_t my_rank = (uint32_t)(ccx + ccy * p.cx);      // == %cluster_ctarank for a (cx, cy, 1) cluster
-    // bytes this CTA receives per refresh: 8 per row from the left / right neighbour, whole rows (all 32 lanes; halo
-    // lanes of a row are overridden by the column boxes) from above / below, 2x8 from each diagonal neighbour
-    const uint32_t expect_bytes = 8u * (uint32_t)(((has_left ? 1 : 0) + (has_right ? 1 : 0)) * (ry1 - ry0 + 1) +
-                                                  ((has_up ? 1 : 0) + (has_down ? 1 : 0)) * kHaloY * 32 +
-                                                  kHaloY * (((has_up && has_left) ? 1 : 0) + ((has_up && has_right) ? 1 : 0) +
-                                                            ((has_down && has_left) ? 1 : 0) + ((has_down && has_right) ? 1 : 0)));
-    const uint32_t sm_base = smem_u32(&sm);
-    using SmemT = Smem<NW, P>;
-    using IG = InboxGeom<TH>;
-    constexpr uint32_t kColbox = offsetof(SmemT, colbox), kRowbox = offsetof(SmemT, rowbox), kHaloBar = offsetof(SmemT, halo_bar);
-    constexpr uint32_t kColPar = sizeof(float) * 2 * TH * 2, kColSide = sizeof(float) * TH * 2;
-    constexpr uint32_t kRowPar = sizeof(float) * 2 * kHaloY * kTileW, kRowSide = sizeof(float) * kHaloY * kTileW;
-
-    TRACE(12);
-    if (hw_cluster) cluster_wait();
-    TRACE(13);
-
-    // ---- T propagation steps ---------------------------------------------------------------------------
-    // Steps come in pairs.  The halo ring received from cluster neighbours is 2 pixels deep, so it is refreshed
-    // at the start of every even step t >= 2; the values it needs (r^t on the rim of each CTA's authoritative
-    // region) are final during the odd step t-1 and are pushed from inside that step's compute phase, row by
-    // row as they complete, so the DSMEM latency hides behind the rest of the step.
-    const bool push_l = multi && lane == 1 && has_left, push_r = multi && lane == 30 && has_right;
-    // Per-lane message of the column push (parity 0 addresses; msg_dst == 0: this lane sends nothing):
-    //   lanes 0..P-1      row i of the left rim column  -> left neighbour's right box
-    //   lanes P..2P-1     row i of the right rim column -> right neighbour's left box
-    //   lanes 2P..2P+3    (top warp)    rows kHaloY.. of the rim columns -> upper-left / upper-right neighbour, bottom box rows
-    //   lanes 2P+4..2P+7  (bottom warp) rows TH-2*kHaloY.. of the rim columns -> lower-left / lower-right neighbour, top box rows
-    static_assert(2 * P + 4 * kHaloY <= 32, "column push needs one lane per message");
-    uint32_t msg_dst = 0u, msg_src = 0u, msg_bar = 0u;
-    if (multi) {
-        const int ty0 = warp * P;
-        int side = -1, srow = 0, drow = 0, dcy = 0;               // side: 0 = my left rim column, 1 = my right rim column
-        if (lane < 2 * P) {
-            side = lane / P; srow = drow = ty0 + lane % P;
-            if (srow < ry0 || srow > ry1) side = -1;
-        } else if (lane < 2 * P + 2 * kHaloY) {
-            if (warp == 0 && has_up) { side = (lane - 2 * P) / kHaloY; const int h = (lane - 2 * P) % kHaloY; srow = kHaloY + h; drow = TH - kHaloY + h; dcy = -1; }
-        } else if (lane < 2 * P + 4 * kHaloY) {
-            if (warp == NW - 1 && has_down) { side = (lane - 2 * P - 2 * kHaloY) / kHaloY; const int h = (lane - 2 * P - 2 * kHaloY) % kHaloY; srow = TH - 2 * kHaloY + h; drow = h; dcy = 1; }
-        }
-        if (side == 0 && !has_left) side = -1;
-        if (side == 1 && !has_right) side = -1;
-        if (side >= 0) {
-            msg_src = (uint32_t)(side * TH + srow) * 8u;
-            if (GLB) {
-                const uint32_t nblk = (blockIdx.z * gridDim.y + blockIdx.y + dcy) * gridDim.x + blockIdx.x + (side == 0 ? -1 : 1);
-                msg_dst = nblk * IG::size + (side == 0 ? IG::col_side : 0u) + (uint32_t)drow;   // uint4 index, parity 0; never 0
-            } else {
-                const uint32_t nb = mapa(sm_base, my_rank + dcy * p.cx + (side == 0 ? -1 : 1));
-                msg_dst = nb + kColbox + (side == 0 ? kColSide : 0u) + 8u * drow;      // my left rim lands in the neighbour's RIGHT box
-                msg_bar = nb + kHaloBar;
-            }
-        }
-    }
-    const uint32_t my_blk = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-
-    auto exchange_rows = [&](int par, u64& top, u64& bot) {
-        // publish this warp's edge rows for the warps above / below (same CTA), fetch theirs
-        *reinterpret_cast<u64*>(&sm.rowbuf[par][warp][0][2 * lane]) = A[0];
-        *reinterpret_cast<u64*>(&sm.rowbuf[par][warp][1][2 * lane]) = A[P - 1];
-        __syncthreads();
-        top = 0ull; bot = 0ull;   // rows -1 and P of this strip (zero above/below the CTA tile)
-        if (warp > 0) top = *reinterpret_cast<const u64*>(&sm.rowbuf[par][warp - 1][1][2 * lane]);
-        if (warp < NW - 1) bot = *reinterpret_cast<const u64*>(&sm.rowbuf[par][warp + 1][0][2 * lane]);
-    };
-
-    // One step, r'(p) = c(p) + sum_j n'_j(p) * r(p + o_j), organised by SOURCE row: row r's three pixel pairs
-    // (x-1,x) / (x,x+1) / (x+1,x+2) are formed once and scattered into the accumulators of output rows
-    // r+1 (taps 0-2), r (taps 3,4) and r-1 (taps 5-7).  Three independent FMA chains are in flight, only one
-    // row of shifted pairs is live, and output row r-1 completes exactly when old row r-1 is dead, so the
-    // update is in place (no second copy of the strip).  PUSH: also send finished rim values to the neighbours.
-    auto compute_step = [&](auto push_tag, u64 top, u64 bot, int rpar, uint32_t tag) {
-        constexpr bool PUSH = decltype(push_tag)::value;
-        (void)tag;
-        const uint32_t bar_off = kHaloBar + 8u * rpar;
-        u64 acc[P];
-#pragma unroll
-        for (int r = -1; r <= P; ++r) {
-            const u64 src = r < 0 ? top : (r < P ? A[r < 0 ? 0 : (r < P ? r : 0)] : bot);
-            u64 s1, s2;
-            shifted(src, s1, s2);
-            if (r + 1 < P) {
-                u64 a = cc[r + 1];
-                a = fma2(nw[r + 1][0], s1, a);
-                a = fma2(nw[r + 1][1], src, a);
-                acc[r + 1] = fma2(nw[r + 1][2], s2, a);
-            }
-            if (r >= 0 && r < P) {
-                u64 a = acc[r];
-                a = fma2(nw[r][3], s1, a);
-                acc[r] = fma2(nw[r][4], s2, a);
-            }
-            if (r >= 1) {
-                const int i = r - 1;
-                u64 a = acc[i];
-                a = fma2(nw[i][5], s1, a);
-                a = fma2(nw[i][6], src, a);
-                a = fma2(nw[i][7], s2, a);
-                A[i] = a;
-                if (PUSH) {
-                    // stage the rim values locally (predicated stores, no branches); shipped in bulk after the sweep
-                    const int ty = warp * P + i;
-                    if (push_l) sm.colstage[rpar][0][ty] = a;
-                    if (push_r) sm.colstage[rpar][1][ty] = a;
-                }
-            }
-        }
-        if (PUSH) {
-            TRACE(90);
-            // ship: the warp's rim columns were staged by lanes 1 / 30; now lane m sends message m (one 8-byte
-            // st.async each, a single warp-wide instruction), rim rows go out directly from all 32 lanes
-            __syncwarp();
-            if (msg_dst != 0u) {
-                const u64 v = *reinterpret_cast<const u64*>(reinterpret_cast<const unsigned char*>(&sm.colstage[rpar][0][0]) + msg_src);
-                if (GLB) st_ll(p.inbox + msg_dst + rpar * IG::col_par, v, tag);
-                else st_async_b64(msg_dst + rpar * kColPar, v, msg_bar + 8u * rpar);
-            }
-            TRACE(91);
-            if (has_up && warp == 0) {                                                   // warp-uniform
-                // my tile rows kHaloY .. 2*kHaloY-1 are the upper neighbour's bottom halo rows
-                if (GLB) {
-                    uint4* d = p.inbox + (size_t)(my_blk - gridDim.x) * IG::size + IG::row_base + rpar * IG::row_par + IG::row_side + lane;
-#pragma unroll
-                    for (int h = 0; h < kHaloY; ++h) st_ll(d + h * 32, A[kHaloY + h], tag);
-                } else {
-                    const uint32_t d = mapa(sm_base, my_rank - p.cx);
-#pragma unroll
-                    for (int h = 0; h < kHaloY; ++h)
-                        st_async_b64(d + kRowbox + rpar * kRowPar + kRowSide + 4u * (h * kTileW + 2 * lane), A[kHaloY + h], d + bar_off);
-                }
-            }
-            if (has_down && warp == NW - 1) {
-                if (GLB) {
-                    uint4* d = p.inbox + (size_t)(my_blk + gridDim.x) * IG::size + IG::row_base + rpar * IG::row_par + lane;
-#pragma unroll
-                    for (int h = 0; h < kHaloY; ++h) st_ll(d + h * 32, A[P - 2 * kHaloY + h], tag);
-                } else {
-                    const uint32_t d = mapa(sm_base, my_rank + p.cx);
-#pragma unroll
-                    for (int h = 0; h < kHaloY; ++h)
-                        st_async_b64(d + kRowbox + rpar * kRowPar + 4u * (h * kTileW + 2 * lane), A[P - 2 * kHaloY + h], d + bar_off);
-                }
-            }
-            TRACE(92);
-        }
-    };
-
-    bool poisoned = false;
-    for (int t = 0; t < p.iters; t += 2) {
-        // ===== even step t =====
-        const int e = t / kPeriod, rpar = e & 1;
-        u64 top, bot;
-        if (t < 24) TRACE(16 + 3 * t);
-        exchange_rows(0, top, bot);
-        if (t < 24) TRACE(17 + 3 * t);
-        if (multi && t > 0) {
-            // take the refreshed halo ring (pushed by the neighbours during their step t-1)
-            if (GLB) {
-                // poll this warp's slots of the global inbox until every tag is current, then drop the payload into
-                // the same shared-memory boxes the DSMEM path fills.  Lanes 0..P+1: left column rows ty0-1..ty0+P,
-                // lanes 16..16+P+1: right column; top / bottom warp: both halo rows, one slot per lane.
-                const uint32_t tag = p.tag_base + (uint32_t)e;
-                const uint4* box = p.inbox + (size_t)my_blk * IG::size;
-                const int sd = lane >> 4, row = warp * P - 1 + (lane & 15);
-                const bool want = (lane & 15) < P + 2 && row >= 0 && row < TH && (sd == 0 ? has_left : has_right);
-                const bool wr0 = has_up && warp == 0, wr1 = has_down && warp == NW - 1;
-                const uint4* cslot = box + rpar * IG::col_par + sd * IG::col_side + (want ? row : 0);
-                const uint4* rslot = box + IG::row_base + rpar * IG::row_par + (wr1 ? IG::row_side : 0u) + lane;
-                uint4 c = make_uint4(0, tag, 0, tag), r0 = c, r1 = c;
-                for (int spin = 0;; ++spin) {
-                    if (want) c = ld_ll(cslot);
-                    if (wr0 || wr1) { r0 = ld_ll(rslot); r1 = ld_ll(rslot + 32); }
-                    const bool ok = c.y == tag && c.w == tag && r0.y == tag && r0.w == tag && r1.y == tag && r1.w == tag;
-                    if (__all_sync(0xffffffffu, ok)) break;
-                    if (spin > (1 << 22)) { poisoned = true; break; }     // neighbours never showed up (grid not co-resident?): fail loudly, do not hang
-                }
-                if (want) *reinterpret_cast<uint2*>(&sm.colbox[rpar][sd][row][0]) = make_uint2(c.x, c.z);
-                if (wr0 || wr1) {
-                    *reinterpret_cast<uint2*>(&sm.rowbox[rpar][wr1 ? 1 : 0][0][2 * lane]) = make_uint2(r0.x, r0.z);
-                    *reinterpret_cast<uint2*>(&sm.rowbox[rpar][wr1 ? 1 : 0][1][2 * lane]) = make_uint2(r1.x, r1.z);
-                }
-                __syncwarp();
-            } else {
-                mbar_wait(sm_base + kHaloBar + 8u * rpar, (uint32_t)(((e - 1) >> 1) & 1));
-            }
-            if (has_up && warp == 0) {
-#pragma unroll
-                for (int h = 0; h < kHaloY; ++h) A[h] = *reinterpret_cast<const u64*>(&sm.rowbox[rpar][0][h][2 * lane]);
-            }
-            if (has_down && warp == NW - 1) {
-#pragma unroll
-                for (int h = 0; h < kHaloY; ++h) A[P - kHaloY + h] = *reinterpret_cast<const u64*>(&sm.rowbox[rpar][1][h][2 * lane]);
-            }
-            const bool edge = (lane == 0 && has_left) || (lane == 31 && has_right);
-            if (edge) {
-                const int side = lane == 0 ? 0 : 1;
-                const int ty0 = warp * P;
-#pragma unroll
-                for (int i = 0; i < P; ++i) A[i] = *reinterpret_cast<const u64*>(&sm.colbox[rpar][side][ty0 + i][0]);
-                top = ty0 > 0 ? *reinterpret_cast<const u64*>(&sm.colbox[rpar][side][ty0 - 1][0]) : 0ull;
-                bot = ty0 + P < TH ? *reinterpret_cast<const u64*>(&sm.colbox[rpar][side][ty0 + P][0]) : 0ull;
-            }
-        }
-        if (t < 24) TRACE(18 + 3 * t);
-        compute_step(std::false_type{}, top, bot, 0, 0u);
-        if (t + 1 >= p.iters) break;
-        // ===== odd step t+1: its results feed the refresh at step t+2 =====
-        if (t < 23) TRACE(16 + 3 * (t + 1));
-        exchange_rows(1, top, bot);
-        if (t < 23) { TRACE(17 + 3 * (t + 1)); TRACE(18 + 3 * (t + 1)); }
-        if (multi && t + 2 < p.iters) {
-            const int rnext = (e + 1) & 1;
-            if (!GLB && threadIdx.x == 0) mbar_arrive_expect_tx(sm_base + kHaloBar + 8u * rnext, expect_bytes);
-            TRACE(89);
-            compute_step(std::true_type{}, top, bot, rnext, p.tag_base + (uint32_t)(e + 1));
-        } else {
-            compute_step(std::false_type{}, top, bot, 0, 0u);
-        }
-    }
-
-    TRACE(14);
-    if (GLB && multi) {
-        // every message addressed to this CTA has been consumed: leave the inbox clean for the next launch / graph replay
-        __syncthreads();
-        uint4* box = p.inbox + (size_t)my_blk * IG::size;
-        for (uint32_t i = threadIdx.x; i < IG::size; i += NW * 32) box[i] = make_uint4(0, 0, 0, 0);
-    }
-    // ---- epilogue: only the final depth goes back to HBM, and only from the pixels this CTA is authoritative for
-    const int vx0 = tix > 0 ? tix * p.stepx + p.margin : 0;
-    const int vx1 = tix == p.ntx - 1 ? W : tix * p.stepx + p.ew - p.margin;
-    const int vy0 = tiy > 0 ? tiy * p.stepy + p.margin : 0;
-    const int vy1 = tiy == p.nty - 1 ? H : tiy * p.stepy + p.eh - p.margin;
-    T* ob = p.out + (size_t)plane * hw;
-    if (poisoned) {
-#pragma unroll
-        for (int i = 0; i < P; ++i) A[i] = pk(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000));
-    }
-    if (lane_auth) {
-        const bool ok0 = gx >= vx0 && gx < vx1 && gx < W, ok1 = gx + 1 >= vx0 && gx + 1 < vx1 && gx + 1 < W;
-#pragma unroll
-        for (int i = 0; i < P; ++i) {
-            const int ty = warp * P + i, gy = gy0 + i;
-            if (ty < ry0 || ty > ry1 || gy < vy0 || gy >= vy1 || gy >= H) continue;
-            const size_t off = (size_t)gy * W + gx;
-            if (ok0 && ok1 && vec_ok) {
-                if (sizeof(T) == 4) *reinterpret_cast<float2*>(ob + off) = make_float2(lo_of(A[i]), hi_of(A[i]));
-                else *reinterpret_cast<__half2*>(ob + off) = __floats2half2_rn(lo_of(A[i]), hi_of(A[i]));
-            } else {
-                if (ok0) ob[off] = from_f32<T>(lo_of(A[i]));
-                if (ok1) ob[off + 1] = from_f32<T>(hi_of(A[i]));
-            }
-        }
-    }
-    TRACE(15);
-}
-
-// ---- host side: pick the cluster shape and the tiling ----------------------------------------------------
-constexpr int kP = 10, kNW = 8;               // 64 x 80 pixel register tile per CTA
-constexpr int kTH = kNW * kP, kStepY = kTH - 2 * kHaloY;
-
-struct Tiling { int cx, cy, ntx, nty, stepx, stepy, ew, eh; long ctas; bool ok; };
-
-inline int tiles_needed(int extent, int size, int margin, int* step)
-{
-    if (extent >= size) { *step = extent; return 1; }     // one tile reaches both image borders
-    const int s = extent - 2 * margin;
-    *step = s;
-    if (s <= 0) return -1;
-    // tile i covers [i*s, i*s + extent); the last one must reach the image border
-    return (size - extent + s - 1) / s + 1;
-}
-
-Tiling choose_tiling(int H, int W, int iters)
-{
-    Tiling best{}; best.ok = false; best.ctas = 0;
-    for (int cx = 1; cx <= 16; ++cx)
-        for (int cy = 1; cx * cy <= 16; ++cy) {
-            Tiling t{}; t.cx = cx; t.cy = cy;
-            t.ew = kStepX * (cx - 1) + kTileW; t.eh = kStepY * (cy - 1) + kTH;
-            t.ntx = tiles_needed(t.ew, W, iters, &t.stepx);
-            t.nty = tiles_needed(t.eh, H, iters, &t.stepy);
-            if (t.ntx < 0 || t.nty < 0) continue;
-            if ((t.stepx & 1) != 0) continue;             // keep pixel pairs at even x
-            t.ctas = (long)t.ntx * t.nty * cx * cy; t.ok = true;
-            // fewest CTAs wins; ties go to the smaller cluster (cheaper to place)
-            if (!best.ok || t.ctas < best.ctas || (t.ctas == best.ctas && cx * cy < best.cx * best.cy)) best = t;
-        }
-    return best;
-}
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_tiled()
-{
-    static EncodeTiledFn fn = [] {
-        void* f = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
-        return (EncodeTiledFn)f;
-    }();
-    return fn;
-}
-
-// 4-D view (W, H, 8 channels, B) of the guidance tensor; box = one channel plane of the staging buffer.
-template <typename T, int MODE>
-bool make_guidance_map(const FwdArgs<T>& a, CUtensorMap* map)
-{
-    using St = Stage<T, kTH, MODE>;
-    const size_t es = sizeof(T);
-    if (!encode_tiled()) return false;
-    if (((uintptr_t)a.guidance & 15) || ((size_t)a.W * es) % 16 || ((size_t)a.gbs * es) % 16) return false;
-    const cuuint64_t dims[4] = {(cuuint64_t)a.W, (cuuint64_t)a.H, 8, (cuuint64_t)a.B};
-    const cuuint64_t strides[3] = {(cuuint64_t)a.W * es, (cuuint64_t)a.H * a.W * es, (cuuint64_t)a.gbs * es};
-    const cuuint32_t box[4] = {(cuuint32_t)St::cols, (cuuint32_t)St::rows, 1, 1};
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
-    const CUresult r = encode_tiled()(map, es == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
-                                      const_cast<T*>(a.guidance), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS;
-}
-
-constexpr size_t kInboxBytes = (size_t)InboxGeom<kTH>::size * sizeof(uint4);
-constexpr long kMaxGlobalExchangeCtas = 512;      // upper bound used for the workspace query (device independent)
-
-// Per-device facts needed to choose the exchange transport, queried once.
-struct DeviceFacts { bool valid; int sms; int max_clusters[17]; };
-DeviceFacts& device_facts(int dev)
-{
-    static DeviceFacts facts[64];
-    static std::mutex mu;
-    std::lock_guard<std::mutex> lock(mu);
-    DeviceFacts& f = facts[dev & 63];
-    if (!f.valid) {
-        cudaDeviceGetAttribute(&f.sms, cudaDevAttrMultiProcessorCount, dev);
-        for (int i = 0; i <= 16; ++i) f.max_clusters[i] = -1;
-        f.valid = true;
-    }
-    return f;
-}
-
-template <typename T, int MODE, bool TMA, bool GLB>
-int launch_variant(const FusedParams<T>& p, const CUtensorMap& map, const Tiling& tl, int planes, cudaStream_t stream)
-{
-    auto kern = fused3x3_kernel<T, kP, kNW, MODE, TMA, GLB>;
-    const size_t smem = sizeof(Smem<kNW, kP>) + (TMA ? Stage<T, kTH, MODE>::bytes : 0);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(tl.ntx * tl.cx), (unsigned)(tl.nty * tl.cy), (unsigned)planes);
-    cfg.blockDim = dim3(kNW * 32);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute at[1];
-    if (GLB) {
-        // neighbours talk through global memory and spin on it: every CTA of the grid must be resident
-        at[0].id = cudaLaunchAttributeCooperative;
-        at[0].val.cooperative = 1;
-    } else {
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = (unsigned)tl.cx; at[0].val.clusterDim.y = (unsigned)tl.cy; at[0].val.clusterDim.z = 1;
-    }
-    cfg.attrs = at; cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, kern, p, map);
-    if (e != cudaSuccess) return (int)e;
-    ++call_stats().launches;
-    return 0;
-}
-
-// How many clusters of this shape can be resident at once (1 CTA per SM kernel): decides whether the cluster
-// path would need more than one wave.
-template <typename T, int MODE>
-int max_active_clusters(int dev, const Tiling& tl)
-{
-    DeviceFacts& f = device_facts(dev);
-    const int size = tl.cx * tl.cy;
-    if (f.max_clusters[size] >= 0) return f.max_clusters[size];
-    auto kern = fused3x3_kernel<T, kP, kNW, MODE, true, false>;
-    const size_t smem = sizeof(Smem<kNW, kP>) + Stage<T, kTH, MODE>::bytes;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)tl.cx, (unsigned)tl.cy, 64); cfg.blockDim = dim3(kNW * 32); cfg.dynamicSmemBytes = smem;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = (unsigned)tl.cx; at[0].val.clusterDim.y = (unsigned)tl.cy; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); n = 1 << 20; }
-    f.max_clusters[size] = n;
-    return n;
-}
-
-std::atomic<uint32_t> g_epoch{0x5a17u};
-
-template <typename T, int MODE>
-int launch(const FwdArgs<T>& a, const Tiling& tl)
-{
-    FusedParams<T> p{};
-    p.g = a.guidance; p.gbs = a.gbs; p.depth = a.depth; p.sparse = a.sparse; p.sparse_channels = a.sparse_channels; p.out = a.out;
-    p.C = a.C; p.H = a.H; p.W = a.W; p.iters = a.iters;
-    p.cx = tl.cx; p.cy = tl.cy; p.ntx = tl.ntx; p.nty = tl.nty; p.stepx = tl.stepx; p.stepy = tl.stepy; p.ew = tl.ew; p.eh = tl.eh;
-    p.margin = a.iters;
-    const int planes = a.B * a.C;
-    // Exchange transport: DSMEM inside hardware clusters by default.  When the clusters would not all be resident
-    // at once (e.g. 8 NYU images = 8 clusters of 15 CTAs but the GPU places only 7) while the whole grid of CTAs
-    // would, drop the clusters and exchange through global memory instead: one wave instead of two.
-    bool glb = false;
-    const long ctas = tl.ctas * planes;
-    static const int force = [] { const char* v = getenv("CSPN_EXCHANGE"); return !v ? 0 : (!strcmp(v, "dsmem") ? 1 : (!strcmp(v, "global") ? 2 : 0)); }();   // debugging knob
-    if (force != 1 && tl.cx * tl.cy > 1 && a.ws && a.ws_bytes >= (size_t)ctas * kInboxBytes && ctas <= kMaxGlobalExchangeCtas && a.iters <= 120) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (ctas <= device_facts(dev).sms && (force == 2 || (long)tl.ntx * tl.nty * planes > max_active_clusters<T, MODE>(dev, tl))) glb = true;
-    }
-    if (glb) {
-        p.inbox = (uint4*)a.ws;
-        p.tag_base = g_epoch.fetch_add(1, std::memory_order_relaxed) << 7;      // + refresh index (1..60) is never 0
-    }
-    alignas(64) CUtensorMap map;
-    memset(&map, 0, sizeof map);
-    const bool tma = make_guidance_map<T, MODE>(a, &map);                        // false: unaligned guidance, plain-load prologue
-    if (glb) return tma ? launch_variant<T, MODE, true, true>(p, map, tl, planes, a.stream) : launch_variant<T, MODE, false, true>(p, map, tl, planes, a.stream);
-    return tma ? launch_variant<T, MODE, true, false>(p, map, tl, planes, a.stream) : launch_variant<T, MODE, false, false>(p, map, tl, planes, a.stream);
-}
-
-}  // namespace
 
 #ifdef CSPN_TRACE
 extern "C" __attribute__((visibility("default"))) int cspn_debug_set_trace(void* buf)
@@ -871,29 +11,37 @@ extern "C" __attribute__((visibility("default"))) int cspn_debug_set_trace(void*
 }
 #endif
 
+namespace {
+constexpr int kTHFwd = kNW * kPFwd;
+}
+
 bool fused_supported(int C, int H, int W, int iters, int ksize, int mode)
 {
     (void)C; (void)mode;
     if (ksize != 3 || iters < 1) return false;
     if ((long)H * W > (1l << 30)) return false;
-    return choose_tiling(H, W, iters).ok;
+    return choose_tiling(H, W, iters, kTHFwd).ok;
 }
 
 size_t fused_workspace(int B, int C, int H, int W, int iters)
 {
-    const Tiling tl = choose_tiling(H, W, iters);
+    const Tiling tl = choose_tiling(H, W, iters, kTHFwd);
     if (!tl.ok || tl.cx * tl.cy == 1) return 0;
     const long ctas = tl.ctas * (long)B * C;
-    return ctas <= kMaxGlobalExchangeCtas ? (size_t)ctas * kInboxBytes : 0;     // inboxes of the global-memory exchange
+    return ctas <= kMaxGlobalExchangeCtas ? (size_t)ctas * inbox_bytes<kTHFwd>() : 0;     // inboxes of the global-memory exchange
 }
 
 template <typename T>
 int fused_forward(const FwdArgs<T>& a)
 {
-    const Tiling tl = choose_tiling(a.H, a.W, a.iters);
+    const Tiling tl = choose_tiling(a.H, a.W, a.iters, kTHFwd);
     if (!tl.ok) return CSPN_ERR_BAD_KERNEL_SIZE;
     if ((long)a.B * a.C > 65535) return CSPN_ERR_BAD_SHAPE;
-    return a.mode == CSPN_MODE_NEW ? launch<T, CSPN_MODE_NEW>(a, tl) : launch<T, CSPN_MODE_OURS>(a, tl);
+    FusedParams<T> p{};
+    p.g = a.guidance; p.gbs = a.gbs; p.depth = a.depth; p.sparse = a.sparse; p.sparse_channels = a.sparse_channels; p.out = a.out;
+    p.C = a.C; p.H = a.H; p.W = a.W; p.iters = a.iters;
+    return a.mode == CSPN_MODE_NEW ? launch<T, kPFwd, CSPN_MODE_NEW, false>(p, tl, a.B, a.ws, a.ws_bytes, a.stream)
+                                   : launch<T, kPFwd, CSPN_MODE_OURS, false>(p, tl, a.B, a.ws, a.ws_bytes, a.stream);
 }
 
 template int fused_forward<float>(const FwdArgs<float>&);

@@ -79,7 +79,9 @@ def test_forward_matches_reference_golden(golden, path):
         assert_close_nan(y.cpu().numpy(), case["out"], FWD_ATOL * scale, name)
 
 
-def test_backward_matches_reference_autograd(golden):
+@pytest.mark.parametrize("path", PATHS)
+def test_backward_matches_reference_autograd(golden, path):
+    _lib.load().cspn_set_path(path)
     checked = 0
     for name in _golden_names(golden):
         case = golden[name]
@@ -158,7 +160,9 @@ def test_fp16_io(path):
     assert (err <= np.abs(ref) * 2.0 ** -10 + FWD_ATOL).all(), f"fp16 I/O: max err {err.max():.3e}"
 
 
-def test_fp16_backward_runs_and_is_close():
+@pytest.mark.parametrize("path", PATHS)
+def test_fp16_backward_runs_and_is_close(path):
+    _lib.load().cspn_set_path(path)
     g, d, s = make_inputs(17, 1, 8, 1, 40, 56, density=0.05)
     g16, d16, s16 = (a.astype(np.float16) for a in (g, d, s))
     go = np.random.default_rng(3).standard_normal(d.shape).astype(np.float16)
@@ -169,7 +173,9 @@ def test_fp16_backward_runs_and_is_close():
     assert np.abs(tg.grad.float().cpu().numpy() - gg).max() <= 2e-3 * max(1.0, np.abs(gg).max())
 
 
-def test_backward_vs_oracle_larger():
+@pytest.mark.parametrize("path", PATHS)
+def test_backward_vs_oracle_larger(path):
+    _lib.load().cspn_set_path(path)
     for mode, cg, k, iters in ((0, 12, 3, 24), (1, 8, 3, 24), (1, 24, 5, 12)):
         g, d, s = make_inputs(90 + mode + k, 2, cg, 1, 45, 61, density=0.03)
         go = np.random.default_rng(5).standard_normal(d.shape).astype(np.float32)
@@ -178,6 +184,35 @@ def test_backward_vs_oracle_larger():
         gg, gd = c_oracle.backward(g, d, s, go, iters, k, mode)
         assert_close_nan(td.grad.cpu().numpy(), gd, GRAD_RTOL * max(1.0, np.abs(gd).max()), f"gd mode {mode} k {k}")
         assert_close_nan(tg.grad.cpu().numpy(), gg, GRAD_RTOL * max(1.0, np.abs(gg).max()), f"gg mode {mode} k {k}")
+
+
+def _check_backward(mode, cg, shape, iters, seed, density=0.03, expect_fused=True):
+    b, h, w = shape
+    g, d, s = make_inputs(seed, b, cg, 1, h, w, density=density)
+    go = np.random.default_rng(seed + 1).standard_normal(d.shape).astype(np.float32)
+    y, tg, td = _run(mode, g, d, s, iters, requires_grad=True)
+    y.backward(_cu(go))
+    if expect_fused:
+        assert _lib.load().cspn_last_path() == _lib.PATH_FUSED and _lib.load().cspn_last_launch_count() == 1
+    gg, gd = c_oracle.backward(g, d, s, go, iters, 3, mode, threads=0)
+    what = f"{shape} mode {mode} cg {cg} T {iters}"
+    assert_close_nan(td.grad.cpu().numpy(), gd, GRAD_RTOL * max(1.0, np.abs(gd).max()), "grad_depth " + what)
+    assert_close_nan(tg.grad.cpu().numpy(), gg, GRAD_RTOL * max(1.0, np.abs(gg).max()), "grad_guidance " + what)
+
+
+# The fused backward (one launch: recompute with history + reverse sweep + Jacobians) over the tilings it can take:
+# single CTA, one cluster (DSMEM halo exchange), several cluster tiles with decaying margins, ragged shapes, and
+# a batch large enough that the clusters do not fit in one wave (global-memory halo exchange).
+@pytest.mark.parametrize("shape", [(2, 228, 304), (4, 228, 304), (1, 352, 1216), (3, 97, 131), (1, 64, 64), (2, 65, 257), (1, 3, 1000), (1, 500, 5)])
+def test_fused_backward_shape_grid(shape):
+    for mode, cg in ((0, 12), (1, 8)):
+        _check_backward(mode, cg, shape, 24, seed=shape[1] * shape[2] + mode)
+
+
+@pytest.mark.parametrize("iters", [1, 2, 3, 7, 40])
+def test_fused_backward_iteration_counts(iters):
+    _check_backward(0, 8, (2, 150, 140), iters, seed=iters)
+    _check_backward(1, 8, (1, 70, 200), iters, seed=iters + 100, density=None if iters == 3 else 0.05)
 
 
 # ---- size-independent properties at BASELINE.json's full sizes -------------------------------
