@@ -260,9 +260,13 @@ struct Stage {
 // Shared-memory tiles of the backward pass (they alias the TMA staging buffer, which is dead after the prologue):
 //   wt [8][TH][64]  transposed weights wt_j(q) = n'_{7-j}(q + o_j): the adjoint sweep is then the same gather as the forward
 //   rt [2][TH][64]  r^t tile of the current / next reverse step, fetched from the history scratch with cp.async
+//   stash (placed behind both the staging buffer and the tiles, written by the prologue, read by the epilogue; mode NEW):
+//   sinv [TH][64]   1 / S(p);   sgn [TH][32]  per pixel pair: bit j / 8+j = raw guidance of tap j negative (lo / hi pixel),
+//                                             bit 16+j / 24+j = raw guidance of tap j exactly zero
 template <int TH> struct BwdTiles {
     static constexpr size_t wt_floats = (size_t)8 * TH * kTileW, rt_floats = (size_t)TH * kTileW;
     static constexpr size_t bytes = (wt_floats + 2 * rt_floats) * sizeof(float);
+    static constexpr size_t stash_bytes = (size_t)TH * kTileW * sizeof(float) + (size_t)TH * 32 * sizeof(uint32_t);
 };
 
 template <typename T, int P, int NW, int MODE, bool TMA, bool GLB, bool BWD>
@@ -275,6 +279,9 @@ fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant_
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     Smem<NW, P>& sm = *reinterpret_cast<Smem<NW, P>*>(smem_raw);
     const T* stage = reinterpret_cast<const T*>(smem_raw + sizeof(Smem<NW, P>));
+    constexpr size_t kStashOff = sizeof(Smem<NW, P>) + ((TMA ? St::bytes : 0) > BwdTiles<TH>::bytes ? (TMA ? St::bytes : 0) : BwdTiles<TH>::bytes);
+    float* sinv = reinterpret_cast<float*>(smem_raw + kStashOff);                       // backward only
+    uint32_t* sgn = reinterpret_cast<uint32_t*>(sinv + TH * kTileW);
 
     TRACE(0);
     const bool multi = p.cx * p.cy > 1;
@@ -321,6 +328,11 @@ fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant_
     // internal tap order j: (dy,dx) row-major without the centre; mode NEW channel k = 7 - j reads the
     // guidance AT THE NEIGHBOUR p + o (CSPN_new.py:43-67), mode OURS channel j reads it at p (CSPN_ours.py:37-41).
     u64 nw[P][8], cc[P], A[P];
+    uint32_t sbits[BWD ? P : 1];
+    if (BWD) {
+#pragma unroll
+        for (int i = 0; i < P; ++i) sbits[i] = 0u;
+    }
     const bool x_in0 = gx >= 0 && gx < W, x_in1 = gx + 1 >= 0 && gx + 1 < W;
     const bool vec_ok = (W & 1) == 0;        // pairs start at even x: 8-byte (fp32) / 4-byte (fp16) aligned when W is even
 
@@ -375,7 +387,9 @@ fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant_
 #pragma unroll
                 for (int i = 0; i < P; ++i) {
                     const T* src = sp + (warp * P + i + 1 + dy) * St::cols + x_off + 2 * lane + dx;
-                    nw[i][j] = pk(fabsf(to_f32(src[0])), fabsf(to_f32(src[1])));      // zero-filled outside the image
+                    const float v0 = to_f32(src[0]), v1 = to_f32(src[1]);
+                    nw[i][j] = pk(fabsf(v0), fabsf(v1));                               // zero-filled outside the image
+                    if (BWD) sbits[i] |= (v0 < 0.f ? 1u << j : 0u) | (v1 < 0.f ? 256u << j : 0u) | (v0 == 0.f ? 65536u << j : 0u) | (v1 == 0.f ? 16777216u << j : 0u);
                 }
             } else {
 #pragma unroll
@@ -399,7 +413,10 @@ fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant_
                 const T* src = gb + (size_t)k * hw + (size_t)yy * W + xx;
                 float v0 = (rin && xx >= 0 && xx < W) ? to_f32(src[0]) : 0.f;
                 float v1 = (rin && xx + 1 >= 0 && xx + 1 < W) ? to_f32(src[1]) : 0.f;
-                if (MODE == CSPN_MODE_NEW) { v0 = fabsf(v0); v1 = fabsf(v1); }
+                if (MODE == CSPN_MODE_NEW) {
+                    if (BWD) sbits[i] |= (v0 < 0.f ? 1u << j : 0u) | (v1 < 0.f ? 256u << j : 0u) | (v0 == 0.f ? 65536u << j : 0u) | (v1 == 0.f ? 16777216u << j : 0u);
+                    v0 = fabsf(v0); v1 = fabsf(v1);
+                }
                 nw[i][j] = pk(v0, v1);
             }
         }
@@ -418,8 +435,13 @@ fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant_
             const bool row_in = gy >= 0 && gy < H;
             // n'_j = (1-m) * W_j / S.  S = 0 -> inf -> 0*inf = NaN like the reference's 0/0.  Pixels outside the
             // image are virtual: exactly zero weights and value (the reference's zero padding).
-            const float f0 = (row_in && x_in0) ? (1.f - lo_of(cc[i])) * fast_rcp(lo_of(sum)) : 0.f;
-            const float f1 = (row_in && x_in1) ? (1.f - hi_of(cc[i])) * fast_rcp(hi_of(sum)) : 0.f;
+            const float r0 = fast_rcp(lo_of(sum)), r1 = fast_rcp(hi_of(sum));
+            if (BWD) {
+                *reinterpret_cast<u64*>(sinv + (warp * P + i) * kTileW + 2 * lane) = pk(r0, r1);
+                sgn[(warp * P + i) * 32 + lane] = sbits[i];
+            }
+            const float f0 = (row_in && x_in0) ? (1.f - lo_of(cc[i])) * r0 : 0.f;
+            const float f1 = (row_in && x_in1) ? (1.f - hi_of(cc[i])) * r1 : 0.f;
             scale[i] = pk(f0, f1);
         }
 #pragma unroll
@@ -906,81 +928,104 @@ fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant_
             for (uint32_t i = threadIdx.x; i < IG::size; i += NW * 32) box[i] = make_uint4(0, 0, 0, 0);
         }
 
-        // ---- epilogue: dL/d depth and dL/d guidance for the pixels this CTA is authoritative for.  The guidance is
-        // read again (normalisation / softmax Jacobian, sign of the raw value); A holds G^0.
-        const T* gb = p.g + (size_t)b * p.gbs;
+        // ---- epilogue: dL/d depth and dL/d guidance for the pixels this CTA is authoritative for; A holds G^0.
+        // Mode NEW needs nothing from HBM but the sparse mask: n'_j(p) is read back from the transposed weight tile,
+        // 1/S and the sign of the raw guidance come from the stash the prologue left in shared memory.
+        // Mode OURS reads its 8 guidance values again to redo the softmax (the forward zeroed border taps).
         T* ggb = p.gg + (size_t)b * p.Cg * hw;
         T* gdb = p.gd + (size_t)plane * hw;
         const float qnan = __int_as_float(0x7fc00000);
+        const u64 qnan2 = pk(qnan, qnan), one2 = pk(1.f, 1.f), mone2 = pk(-1.f, -1.f);
         if (lane_auth) {
+            const bool ok0 = gx >= vx0 && gx < vx1 && gx < W, ok1 = gx + 1 >= vx0 && gx + 1 < vx1 && gx + 1 < W;
 #pragma unroll
             for (int i = 0; i < P; ++i) {
                 const int ty = warp * P + i, gy = gy0 + i;
-                if (ty < ry0 || ty > ry1 || gy < vy0 || gy >= vy1 || gy >= H) continue;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int x = gx + h;
-                    if (x < vx0 || x >= vx1 || x >= W) continue;
-                    const size_t off = (size_t)gy * W + x;
-                    const float m = sb ? signf(to_f32(sb[off])) : 0.f;
-                    const float g0 = h ? hi_of(A[i]) : lo_of(A[i]);
-                    const float sg = h ? hi_of(sumG[i]) : lo_of(sumG[i]);
-                    gdb[off] = from_f32<T>(poisoned ? qnan : fmaf(m, sg, g0));
-                    float gq[8];
-                    bool inb[8];
+                if (ty < ry0 || ty > ry1 || gy < vy0 || gy >= vy1 || gy >= H || (!ok0 && !ok1)) continue;
+                const size_t off = (size_t)gy * W + gx;
+                float m0 = 0.f, m1 = 0.f;
+                if (sb) {
+                    if (ok0) m0 = signf(to_f32(sb[off]));
+                    if (ok1) m1 = signf(to_f32(sb[off + 1]));
+                }
+                const u64 m2 = pk(m0, m1);
+                const u64 om = fma2(m2, mone2, one2);                                  // 1 - m
+                u64 gdv = fma2(m2, sumG[i], A[i]);                                     // m * sum_t G^t + G^0
+                if (poisoned) gdv = qnan2;
+                if (ok0) gdb[off] = from_f32<T>(lo_of(gdv));
+                if (ok1) gdb[off + 1] = from_f32<T>(hi_of(gdv));
+                if (MODE == CSPN_MODE_NEW) {
+                    // dL/dW_j(p) = ((1-m) gn'_j - sum_i n'_i gn'_i) / S; it belongs to guidance element (k = 7-j, p + o_j) times
+                    // the sign of that element.  Elements (k, q) whose p = q - o_k is outside the image get 0: that is
+                    // channel j at THIS pixel whenever p + o_j is outside.
+                    const u64 inv = *reinterpret_cast<const u64*>(sinv + ty * kTileW + 2 * lane);
+                    const uint32_t bits = sgn[ty * 32 + lane];
+                    u64 D = 0ull;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const int jj = j < 4 ? j : j + 1;
-                        const int yy = gy + jj / 3 - 1, xx = x + jj % 3 - 1;
-                        inb[j] = yy >= 0 && yy < H && xx >= 0 && xx < W;
-                        gq[j] = (1.f - m) * (h ? hi_of(gn[i][j]) : lo_of(gn[i][j]));
-                        if (poisoned) gq[j] = qnan;
+                        const int tyn = ty + jj / 3 - 1, tx = 2 * lane + jj % 3 - 1;
+                        float n0 = 0.f, n1 = 0.f;
+                        if (tyn >= 0 && tyn < TH) {
+                            const float* w = wt + ((size_t)(7 - j) * TH + tyn) * kTileW;       // wt_{7-j}(p + o_j) = n'_j(p)
+                            if (tx >= 0) n0 = w[tx];
+                            if (tx + 1 < kTileW) n1 = w[tx + 1];
+                        }
+                        D = fma2(pk(n0, n1), gn[i][j], D);
                     }
-                    if (MODE == CSPN_MODE_NEW) {
-                        // W_j(p) = |g_k(p + o_j)|, k = 7 - j; dL/dW_j = (dL/dn_j - sum_i n_i dL/dn_i) / S; the value belongs to
-                        // guidance element (k, p + o_j).  Elements (k, q) whose p = q - o would be outside the image get 0:
-                        // that is channel j at this pixel whenever p + o_j is outside.
-                        float av[8], sv[8];
+                    const u64 negD = D ^ 0x8000000080000000ull;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int jj = j < 4 ? j : j + 1;
-                            const int yy = gy + jj / 3 - 1, xx = x + jj % 3 - 1;
-                            const float v = inb[j] ? to_f32(gb[(size_t)(7 - j) * hw + (size_t)yy * W + xx]) : 0.f;
-                            av[j] = fabsf(v);
-                            sv[j] = signf(v);
-                        }
-                        float S = av[7];
+                    for (int j = 0; j < 8; ++j) {
+                        const int jj = j < 4 ? j : j + 1;
+                        const int yy = gy + jj / 3 - 1, xx = gx + jj % 3 - 1;
+                        u64 gw = mul2(fma2(om, gn[i][j], negD), inv);
+                        if (poisoned) gw = qnan2;
+                        float v0 = lo_of(gw), v1 = hi_of(gw);
+                        v0 = (bits >> j) & 1u ? -v0 : v0;
+                        v0 = (bits >> (16 + j)) & 1u ? 0.f : v0;
+                        v1 = (bits >> (8 + j)) & 1u ? -v1 : v1;
+                        v1 = (bits >> (24 + j)) & 1u ? 0.f : v1;
+                        const bool rin = yy >= 0 && yy < H;
+                        T* dst = ggb + (size_t)(7 - j) * hw + (size_t)yy * W + xx;
+                        T* zer = ggb + (size_t)j * hw + off;
+                        if (ok0) { if (rin && xx >= 0 && xx < W) dst[0] = from_f32<T>(v0); else zer[0] = from_f32<T>(0.f); }
+                        if (ok1) { if (rin && xx + 1 >= 0 && xx + 1 < W) dst[1] = from_f32<T>(v1); else zer[1] = from_f32<T>(0.f); }
+                    }
+                } else {
+                    const T* gb = p.g + (size_t)b * p.gbs + off;
+                    float z0[8], z1[8];
 #pragma unroll
-                        for (int k = 1; k < 8; ++k) S += av[7 - k];
-                        float dot = 0.f;
+                    for (int j = 0; j < 8; ++j) {
+                        z0[j] = ok0 ? to_f32(gb[(size_t)j * hw]) : 0.f;
+                        z1[j] = ok1 ? to_f32(gb[(size_t)j * hw + 1]) : 0.f;
+                    }
+                    float mx0 = z0[0], mx1 = z1[0];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) dot = fmaf(av[j] / S, gq[j], dot);
+                    for (int j = 1; j < 8; ++j) { mx0 = fmaxf(mx0, z0[j]); mx1 = fmaxf(mx1, z1[j]); }
+                    float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int jj = j < 4 ? j : j + 1;
-                            const int yy = gy + jj / 3 - 1, xx = x + jj % 3 - 1;
-                            if (inb[j]) ggb[(size_t)(7 - j) * hw + (size_t)yy * W + xx] = from_f32<T>(sv[j] * (gq[j] - dot) / S);
-                            else ggb[(size_t)j * hw + off] = from_f32<T>(0.f);
-                        }
-                    } else {
-                        float z[8];
+                    for (int j = 0; j < 8; ++j) { z0[j] = expf(z0[j] - mx0); z1[j] = expf(z1[j] - mx1); s0 += z0[j]; s1 += z1[j]; }
+                    const u64 rs2 = pk(fast_rcp(s0), fast_rcp(s1));
+                    u64 sj[8], gq[8], dot = 0ull;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) z[j] = to_f32(gb[(size_t)j * hw + off]);
-                        float mx = z[0];
+                    for (int j = 0; j < 8; ++j) {
+                        const int jj = j < 4 ? j : j + 1;
+                        const int yy = gy + jj / 3 - 1, xx = gx + jj % 3 - 1;
+                        const bool rin = yy >= 0 && yy < H;
+                        sj[j] = mul2(pk(z0[j], z1[j]), rs2);
+                        const u64 q = mul2(om, gn[i][j]);
+                        // taps on the zero padding carry no gradient
+                        gq[j] = pk((rin && xx >= 0 && xx < W) ? lo_of(q) : 0.f, (rin && xx + 1 >= 0 && xx + 1 < W) ? hi_of(q) : 0.f);
+                        dot = fma2(sj[j], gq[j], dot);
+                    }
+                    const u64 negdot = dot ^ 0x8000000080000000ull;
 #pragma unroll
-                        for (int j = 1; j < 8; ++j) mx = fmaxf(mx, z[j]);
-                        float sum = 0.f;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) { z[j] = expf(z[j] - mx); sum += z[j]; }
-                        float dot = 0.f;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            z[j] = z[j] / sum;
-                            if (!inb[j]) gq[j] = 0.f;                 // taps on the zero padding carry no gradient
-                            dot = fmaf(z[j], gq[j], dot);
-                        }
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) ggb[(size_t)j * hw + off] = from_f32<T>(z[j] * (gq[j] - dot));
+                    for (int j = 0; j < 8; ++j) {
+                        u64 o = mul2(sj[j], add2(gq[j], negdot));
+                        if (poisoned) o = qnan2;
+                        T* dst = ggb + (size_t)j * hw + off;
+                        if (ok0) dst[0] = from_f32<T>(lo_of(o));
+                        if (ok1) dst[1] = from_f32<T>(hi_of(o));
                     }
                 }
             }
@@ -1084,7 +1129,7 @@ constexpr size_t fused_smem_bytes()
 {
     constexpr size_t stage = TMA ? Stage<T, kNW * P, MODE>::bytes : 0;
     constexpr size_t tiles = BWD ? BwdTiles<kNW * P>::bytes : 0;
-    return sizeof(Smem<kNW, P>) + (stage > tiles ? stage : tiles);
+    return sizeof(Smem<kNW, P>) + (stage > tiles ? stage : tiles) + (BWD ? BwdTiles<kNW * P>::stash_bytes : 0);
 }
 
 template <typename T, int P, int MODE, bool TMA, bool GLB, bool BWD>
