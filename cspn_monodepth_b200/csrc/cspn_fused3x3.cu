@@ -20,12 +20,12 @@ bool fused_supported(int C, int H, int W, int iters, int ksize, int mode)
     (void)C; (void)mode;
     if (ksize != 3 || iters < 1) return false;
     if ((long)H * W > (1l << 30)) return false;
-    return choose_tiling(H, W, iters, kTHFwd).ok;
+    return choose_tiling(H, W, iters, kTHFwd, 1, default_capacity()).ok;
 }
 
 size_t fused_workspace(int B, int C, int H, int W, int iters)
 {
-    const Tiling tl = choose_tiling(H, W, iters, kTHFwd);
+    const Tiling tl = choose_tiling(H, W, iters, kTHFwd, (long)B * C, capacity<kPFwd, false>());
     if (!tl.ok || tl.cx * tl.cy == 1) return 0;
     const long ctas = tl.ctas * (long)B * C;
     return ctas <= kMaxGlobalExchangeCtas ? (size_t)ctas * inbox_bytes<kTHFwd>() : 0;     // inboxes of the global-memory exchange
@@ -34,7 +34,7 @@ size_t fused_workspace(int B, int C, int H, int W, int iters)
 template <typename T>
 int fused_forward(const FwdArgs<T>& a)
 {
-    const Tiling tl = choose_tiling(a.H, a.W, a.iters, kTHFwd);
+    const Tiling tl = choose_tiling(a.H, a.W, a.iters, kTHFwd, (long)a.B * a.C, capacity<kPFwd, false>());
     if (!tl.ok) return CSPN_ERR_BAD_KERNEL_SIZE;
     if ((long)a.B * a.C > 65535) return CSPN_ERR_BAD_SHAPE;
     FusedParams<T> p{};

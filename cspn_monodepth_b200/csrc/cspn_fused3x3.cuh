@@ -1040,6 +1040,7 @@ constexpr int kPFwd = 10;                     // forward: 64 x 80 pixel register
 constexpr int kPBwd = 8;                      // backward: 64 x 64 (twice the per-pixel register state)
 constexpr int kHistSlots = 192;               // history scratch tiles, indexed by %smid (B200: 148 SMs; guarded in the kernel)
 
+constexpr long kMaxGlobalExchangeCtas = 512;      // upper bound on the grid of the global-memory exchange
 struct Tiling { int cx, cy, ntx, nty, stepx, stepy, ew, eh; long ctas; bool ok; };
 
 inline int tiles_needed(int extent, int size, int margin, int* step)
@@ -1052,13 +1053,26 @@ inline int tiles_needed(int extent, int size, int margin, int* step)
     return (size - extent + s - 1) / s + 1;
 }
 
-// th = rows of one CTA tile (kNW * P)
-inline Tiling choose_tiling(int H, int W, int iters, int th)
+// What the GPU can hold at once (1 CTA per SM kernels): SM count and, per hardware cluster size, how many clusters
+// are co-resident.  Defaults = B200 as measured with tools/microbench/clusters.cu (GPCs of different sizes make
+// large clusters expensive: 7 clusters of 11-16 CTAs, 15 of 7-9, 26 of 5); refined per device at run time.
+struct Capacity { int sms; int clusters[17]; };
+inline Capacity default_capacity()
+{
+    return Capacity{148, {0, 148, 74, 45, 33, 26, 22, 15, 15, 15, 11, 7, 7, 7, 7, 7, 7}};
+}
+
+// th = rows of one CTA tile (kNW * P); planes = independent images (B * C).  Picks the cluster shape / tile grid that
+// needs the fewest waves: CTAs / (CTAs the GPU holds at once for that cluster size).  A grid that fits on the GPU in
+// one piece does not need hardware clusters at all (global-memory halo exchange under a cooperative launch), so
+// there the cluster may have any shape up to the whole image and the fewest CTAs win.
+inline Tiling choose_tiling(int H, int W, int iters, int th, long planes, const Capacity& cap)
 {
     const int step_y = th - 2 * kHaloY;
     Tiling best{}; best.ok = false; best.ctas = 0;
+    double best_cost = 0.0;
     for (int cx = 1; cx <= 16; ++cx)
-        for (int cy = 1; cx * cy <= 16; ++cy) {
+        for (int cy = 1; cy <= 16; ++cy) {
             Tiling t{}; t.cx = cx; t.cy = cy;
             t.ew = kStepX * (cx - 1) + kTileW; t.eh = step_y * (cy - 1) + th;
             t.ntx = tiles_needed(t.ew, W, iters, &t.stepx);
@@ -1066,8 +1080,18 @@ inline Tiling choose_tiling(int H, int W, int iters, int th)
             if (t.ntx < 0 || t.nty < 0) continue;
             if ((t.stepx & 1) != 0) continue;             // keep pixel pairs at even x
             t.ctas = (long)t.ntx * t.nty * cx * cy; t.ok = true;
-            // fewest CTAs wins; ties go to the smaller cluster (cheaper to place)
-            if (!best.ok || t.ctas < best.ctas || (t.ctas == best.ctas && cx * cy < best.cx * best.cy)) best = t;
+            const long total = t.ctas * planes;
+            const bool one_piece = cx * cy > 1 && total <= cap.sms && total <= kMaxGlobalExchangeCtas;
+            if (cx * cy > 16 && !one_piece) continue;     // hardware clusters hold at most 16 CTAs
+            const long held = one_piece ? cap.sms : (long)cap.clusters[cx * cy] * cx * cy;
+            if (held <= 0) continue;
+            double cost = (double)total / (double)held;
+            if (cost < 1.0) cost = 1.0;
+            // fewest waves win; ties go to fewer CTAs, then to the smaller cluster (cheaper to place)
+            if (!best.ok || cost < best_cost - 1e-9 ||
+                (cost < best_cost + 1e-9 && (t.ctas < best.ctas || (t.ctas == best.ctas && cx * cy < best.cx * best.cy)))) {
+                best = t; best_cost = cost;
+            }
         }
     return best;
 }
@@ -1106,10 +1130,9 @@ bool make_guidance_map(const T* guidance, int64_t gbs, int B, int H, int W, CUte
 }
 
 template <int TH> constexpr size_t inbox_bytes() { return (size_t)InboxGeom<TH>::size * sizeof(uint4); }
-constexpr long kMaxGlobalExchangeCtas = 512;      // upper bound used for the workspace query (device independent)
 
 // Per-device facts needed to choose the exchange transport, queried once.
-struct DeviceFacts { bool valid; int sms; int max_clusters[2][17]; };
+struct DeviceFacts { bool valid; int sms; int max_clusters[2][17]; bool cap_valid[2]; Capacity cap[2]; };
 inline DeviceFacts& device_facts(int dev)
 {
     static DeviceFacts facts[64];
@@ -1119,6 +1142,7 @@ inline DeviceFacts& device_facts(int dev)
     if (!f.valid) {
         cudaDeviceGetAttribute(&f.sms, cudaDevAttrMultiProcessorCount, dev);
         for (int i = 0; i <= 16; ++i) f.max_clusters[0][i] = f.max_clusters[1][i] = -1;
+        f.cap_valid[0] = f.cap_valid[1] = false;
         f.valid = true;
     }
     return f;
@@ -1162,28 +1186,42 @@ int launch_variant(const FusedParams<T>& p, const CUtensorMap& map, const Tiling
     return 0;
 }
 
-// How many clusters of this shape can be resident at once (1 CTA per SM kernel): decides whether the cluster
-// path would need more than one wave.
+// How many clusters of `size` CTAs can be resident at once (1 CTA per SM kernel).
 template <typename T, int P, int MODE, bool BWD>
-int max_active_clusters(int dev, const Tiling& tl)
+int max_active_clusters(int dev, int size)
 {
     DeviceFacts& f = device_facts(dev);
-    const int size = tl.cx * tl.cy;
     if (f.max_clusters[BWD][size] >= 0) return f.max_clusters[BWD][size];
     auto kern = fused3x3_kernel<T, P, kNW, MODE, true, false, BWD>;
     constexpr size_t smem = fused_smem_bytes<T, P, MODE, true, BWD>();
     cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)tl.cx, (unsigned)tl.cy, 64); cfg.blockDim = dim3(kNW * 32); cfg.dynamicSmemBytes = smem;
+    cfg.gridDim = dim3((unsigned)size, 1, 64); cfg.blockDim = dim3(kNW * 32); cfg.dynamicSmemBytes = smem;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = (unsigned)tl.cx; at[0].val.clusterDim.y = (unsigned)tl.cy; at[0].val.clusterDim.z = 1;
+    at[0].val.clusterDim.x = (unsigned)size; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); n = 1 << 20; }
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); n = default_capacity().clusters[size]; }
     f.max_clusters[BWD][size] = n;
     return n;
+}
+
+// Capacity of the current device for the forward (BWD = false, P = kPFwd) or backward kernel; the B200 defaults when
+// there is no usable device (workspace queries on a machine without a GPU).
+template <int P, bool BWD>
+Capacity capacity()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return default_capacity(); }
+    DeviceFacts& f = device_facts(dev);
+    if (f.cap_valid[BWD]) return f.cap[BWD];
+    if (f.sms <= 0) { cudaGetLastError(); return default_capacity(); }
+    Capacity c{}; c.sms = f.sms; c.clusters[0] = 0;
+    for (int size = 1; size <= 16; ++size) c.clusters[size] = max_active_clusters<float, P, CSPN_MODE_NEW, BWD>(dev, size);
+    f.cap[BWD] = c; f.cap_valid[BWD] = true;
+    return c;
 }
 
 inline std::atomic<uint32_t>& exchange_epoch()
@@ -1210,8 +1248,9 @@ int launch(FusedParams<T> p, const Tiling& tl, int B, void* inbox, size_t inbox_
     if (force != 1 && tl.cx * tl.cy > 1 && inbox && inbox_avail >= (size_t)ctas * inbox_bytes<TH>() && ctas <= kMaxGlobalExchangeCtas && p.iters <= 60) {
         int dev = 0;
         cudaGetDevice(&dev);
-        if (ctas <= device_facts(dev).sms && (force == 2 || (long)tl.ntx * tl.nty * planes > max_active_clusters<T, P, MODE, BWD>(dev, tl))) glb = true;
+        if (ctas <= device_facts(dev).sms && (force == 2 || tl.cx * tl.cy > 16 || (long)tl.ntx * tl.nty * planes > max_active_clusters<T, P, MODE, BWD>(dev, tl.cx * tl.cy))) glb = true;
     }
+    if (!glb && tl.cx * tl.cy > 16) return CSPN_ERR_WORKSPACE;      // this tiling only exists for the global-memory exchange
     if (glb) {
         p.inbox = (uint4*)inbox;
         p.tag_base = exchange_epoch().fetch_add(1, std::memory_order_relaxed) << 7;      // + refresh index (1..120) is never 0

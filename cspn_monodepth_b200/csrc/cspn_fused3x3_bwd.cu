@@ -23,13 +23,13 @@ bool fused_bwd_supported(int C, int H, int W, int iters, int ksize, int mode)
     // one depth channel (the gradient of the shared affinity would otherwise sum over channels), refresh tags fit 7 bits
     if (C != 1 || ksize != 3 || iters < 1 || iters > 60) return false;
     if ((long)H * W > (1l << 30)) return false;
-    return choose_tiling(H, W, iters, kTHBwd).ok;
+    return choose_tiling(H, W, iters, kTHBwd, 1, default_capacity()).ok;
 }
 
 size_t fused_bwd_workspace(int B, int C, int H, int W, int iters)
 {
     (void)C;
-    const Tiling tl = choose_tiling(H, W, iters, kTHBwd);
+    const Tiling tl = choose_tiling(H, W, iters, kTHBwd, (long)B, capacity<kPBwd, true>());
     if (!tl.ok) return 0;
     return bwd_inbox_bytes(tl, B) + hist_bytes(iters);
 }
@@ -37,7 +37,7 @@ size_t fused_bwd_workspace(int B, int C, int H, int W, int iters)
 template <typename T>
 int fused_backward(const BwdArgs<T>& a)
 {
-    const Tiling tl = choose_tiling(a.H, a.W, a.iters, kTHBwd);
+    const Tiling tl = choose_tiling(a.H, a.W, a.iters, kTHBwd, (long)a.B, capacity<kPBwd, true>());
     if (!tl.ok || a.C != 1) return CSPN_ERR_BAD_KERNEL_SIZE;
     if ((long)a.B > 65535) return CSPN_ERR_BAD_SHAPE;
     const size_t inbox = bwd_inbox_bytes(tl, a.B);
