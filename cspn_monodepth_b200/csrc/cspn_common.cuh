@@ -80,7 +80,13 @@ size_t generic_bwd_workspace(int B, int C, int H, int W, int iters, int taps);
 template <typename T> int generic_forward(const FwdArgs<T>& a, const TapTable& tt);
 template <typename T> int generic_backward(const BwdArgs<T>& a, const TapTable& tt);
 
-// fused path (cspn_fused3x3.cu): whole recurrence in one launch, 3x3 only
+// ---- fused path: whole recurrence in one launch, 3x3 only (cspn_fused3x3*.cu) -------------------------------
+constexpr long kMaxGlobalExchangeCtas = 512;      // upper bound on the grid of the global-memory halo exchange
+// Cluster shape (cx x cy CTAs) and grid of cluster tiles (ntx x nty per image) covering an image.
+struct Tiling { int cx, cy, ntx, nty, stepx, stepy, ew, eh; long ctas; bool ok; };
+// What the GPU holds at once for one kernel configuration: sms = CTA slots of the whole GPU (SMs x resident CTAs per
+// SM), clusters[n] = co-resident hardware clusters of n CTAs.
+struct Capacity { int sms; int clusters[17]; };
 bool fused_supported(int C, int H, int W, int iters, int ksize, int mode);
 template <typename T> int fused_forward(const FwdArgs<T>& a);
 size_t fused_workspace(int B, int C, int H, int W, int iters);   // optional scratch (0 = none)

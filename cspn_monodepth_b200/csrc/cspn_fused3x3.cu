@@ -1,4 +1,5 @@
-// Forward instantiations and host entry points of the fused 3x3 CSPN kernel (cspn_fused3x3.cuh).
+// Forward host entry points of the fused 3x3 CSPN kernel (cspn_fused3x3.cuh) and its forward instantiations
+// (64 x 80 pixel register tile, 8 warps, one CTA per SM).
 #include "cspn_fused3x3.cuh"
 
 namespace cspn {
@@ -12,36 +13,39 @@ extern "C" __attribute__((visibility("default"))) int cspn_debug_set_trace(void*
 #endif
 
 namespace {
-constexpr int kTHFwd = kNW * kPFwd;
+constexpr int kTHBig = kNW * kPFwd;
+
+Tiling plan_forward(int B, int C, int H, int W, int iters)
+{
+    return choose_tiling(H, W, iters, kTHBig, (long)B * C, capacity<kPFwd, kNW, false>());
 }
+}  // namespace
 
 bool fused_supported(int C, int H, int W, int iters, int ksize, int mode)
 {
     (void)C; (void)mode;
     if (ksize != 3 || iters < 1) return false;
     if ((long)H * W > (1l << 30)) return false;
-    return choose_tiling(H, W, iters, kTHFwd, 1, default_capacity()).ok;
+    return choose_tiling(H, W, iters, kTHBig, 1, default_capacity()).ok;
 }
 
 size_t fused_workspace(int B, int C, int H, int W, int iters)
 {
-    const Tiling tl = choose_tiling(H, W, iters, kTHFwd, (long)B * C, capacity<kPFwd, false>());
+    const Tiling tl = plan_forward(B, C, H, W, iters);
     if (!tl.ok || tl.cx * tl.cy == 1) return 0;
     const long ctas = tl.ctas * (long)B * C;
-    return ctas <= kMaxGlobalExchangeCtas ? (size_t)ctas * inbox_bytes<kTHFwd>() : 0;     // inboxes of the global-memory exchange
+    return ctas <= kMaxGlobalExchangeCtas ? (size_t)ctas * inbox_bytes<kTHBig>() : 0;     // inboxes of the global-memory exchange
 }
 
 template <typename T>
 int fused_forward(const FwdArgs<T>& a)
 {
-    const Tiling tl = choose_tiling(a.H, a.W, a.iters, kTHFwd, (long)a.B * a.C, capacity<kPFwd, false>());
+    const Tiling tl = plan_forward(a.B, a.C, a.H, a.W, a.iters);
     if (!tl.ok) return CSPN_ERR_BAD_KERNEL_SIZE;
     if ((long)a.B * a.C > 65535) return CSPN_ERR_BAD_SHAPE;
-    FusedParams<T> p{};
-    p.g = a.guidance; p.gbs = a.gbs; p.depth = a.depth; p.sparse = a.sparse; p.sparse_channels = a.sparse_channels; p.out = a.out;
-    p.C = a.C; p.H = a.H; p.W = a.W; p.iters = a.iters;
-    return a.mode == CSPN_MODE_NEW ? launch<T, kPFwd, CSPN_MODE_NEW, false>(p, tl, a.B, a.ws, a.ws_bytes, a.stream)
-                                   : launch<T, kPFwd, CSPN_MODE_OURS, false>(p, tl, a.B, a.ws, a.ws_bytes, a.stream);
+    FusedParams<T> p = forward_params(a);
+    return a.mode == CSPN_MODE_NEW ? launch<T, kPFwd, kNW, CSPN_MODE_NEW, false>(p, tl, a.B, a.ws, a.ws_bytes, a.stream)
+                                   : launch<T, kPFwd, kNW, CSPN_MODE_OURS, false>(p, tl, a.B, a.ws, a.ws_bytes, a.stream);
 }
 
 template int fused_forward<float>(const FwdArgs<float>&);

@@ -270,7 +270,7 @@ template <int TH> struct BwdTiles {
 };
 
 template <typename T, int P, int NW, int MODE, bool TMA, bool GLB, bool BWD>
-__global__ void __launch_bounds__(NW * 32, 1)
+__global__ void __launch_bounds__(NW * 32, (NW <= 5 ? 2 : 1))
 fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant__ CUtensorMap gmap)
 {
     constexpr int TH = NW * P;
@@ -633,27 +633,43 @@ fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant_
 
     // Take the refreshed halo ring of refresh epoch e (pushed by the neighbours during their previous step).
     bool poisoned = false;
-    auto take_refresh = [&](int e, u64& top, u64& bot) {
+    // GLB exchange: this warp's slots of the global inbox.  Lanes 0..P+1: left column rows ty0-1..ty0+P, lanes
+    // 16..16+P+1: right column; top / bottom warp: both halo rows, one slot per lane.
+    struct Polled { uint4 c, r0, r1; };
+    const int poll_sd = lane >> 4, poll_row = warp * P - 1 + (lane & 15);
+    const bool poll_want = (lane & 15) < P + 2 && poll_row >= 0 && poll_row < TH && (poll_sd == 0 ? has_left : has_right);
+    const bool poll_r0 = has_up && warp == 0, poll_r1 = has_down && warp == NW - 1;
+    // One read of the slots of refresh epoch e.  Issued BEFORE the intra-CTA row exchange of the step so that the L2
+    // round trip overlaps that barrier; take_refresh only re-reads what was not current yet.
+    auto poll = [&](int e) {
+        const uint32_t tag = p.tag_base + (uint32_t)e;
+        const int rpar = e & 1;
+        Polled q;
+        q.c = make_uint4(0, tag, 0, tag); q.r0 = q.c; q.r1 = q.c;
+        if (GLB) {
+            const uint4* box = p.inbox + (size_t)my_blk * IG::size;
+            if (poll_want) q.c = ld_ll(box + rpar * IG::col_par + poll_sd * IG::col_side + poll_row);
+            if (poll_r0 || poll_r1) {
+                const uint4* rslot = box + IG::row_base + rpar * IG::row_par + (poll_r1 ? IG::row_side : 0u) + lane;
+                q.r0 = ld_ll(rslot); q.r1 = ld_ll(rslot + 32);
+            }
+        }
+        return q;
+    };
+    auto take_refresh = [&](int e, Polled q, u64& top, u64& bot) {
         const int rpar = e & 1;
         if (GLB) {
-            // poll this warp's slots of the global inbox until every tag is current, then drop the payload into
-            // the same shared-memory boxes the DSMEM path fills.  Lanes 0..P+1: left column rows ty0-1..ty0+P,
-            // lanes 16..16+P+1: right column; top / bottom warp: both halo rows, one slot per lane.
+            // wait until every tag is current, then drop the payload into the same shared-memory boxes the DSMEM path fills
             const uint32_t tag = p.tag_base + (uint32_t)e;
-            const uint4* box = p.inbox + (size_t)my_blk * IG::size;
-            const int sd = lane >> 4, row = warp * P - 1 + (lane & 15);
-            const bool want = (lane & 15) < P + 2 && row >= 0 && row < TH && (sd == 0 ? has_left : has_right);
-            const bool wr0 = has_up && warp == 0, wr1 = has_down && warp == NW - 1;
-            const uint4* cslot = box + rpar * IG::col_par + sd * IG::col_side + (want ? row : 0);
-            const uint4* rslot = box + IG::row_base + rpar * IG::row_par + (wr1 ? IG::row_side : 0u) + lane;
-            uint4 c = make_uint4(0, tag, 0, tag), r0 = c, r1 = c;
+            const int sd = poll_sd, row = poll_row;
+            const bool want = poll_want, wr0 = poll_r0, wr1 = poll_r1;
             for (int spin = 0;; ++spin) {
-                if (want) c = ld_ll(cslot);
-                if (wr0 || wr1) { r0 = ld_ll(rslot); r1 = ld_ll(rslot + 32); }
-                const bool ok = c.y == tag && c.w == tag && r0.y == tag && r0.w == tag && r1.y == tag && r1.w == tag;
+                const bool ok = q.c.y == tag && q.c.w == tag && q.r0.y == tag && q.r0.w == tag && q.r1.y == tag && q.r1.w == tag;
                 if (__all_sync(0xffffffffu, ok)) break;
                 if (spin > (1 << 22)) { poisoned = true; break; }     // neighbours never showed up (grid not co-resident?): fail loudly, do not hang
+                q = poll(e);
             }
+            const uint4 c = q.c, r0 = q.r0, r1 = q.r1;
             if (want) *reinterpret_cast<uint2*>(&sm.colbox[rpar][sd][row][0]) = make_uint2(c.x, c.z);
             if (wr0 || wr1) {
                 *reinterpret_cast<uint2*>(&sm.rowbox[rpar][wr1 ? 1 : 0][0][2 * lane]) = make_uint2(r0.x, r0.z);
@@ -709,9 +725,11 @@ fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant_
         const int e = t / kPeriod;
         u64 top, bot;
         if (t < 24) TRACE(16 + 3 * t);
+        Polled pq{};
+        if (GLB && multi && t > 0) pq = poll(e);
         exchange_rows(0, top, bot);
         if (t < 24) TRACE(17 + 3 * t);
-        if (multi && t > 0) take_refresh(e, top, bot);
+        if (multi && t > 0) take_refresh(e, pq, top, bot);
         if (t < 24) TRACE(18 + 3 * t);
         dump_hist(t);
         if (BWD && t + 1 >= p.iters) break;
@@ -903,10 +921,12 @@ fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant_
             // ===== even reverse step s (t = T-1-s) =====
             const int e = EF + s / kPeriod;
             u64 top, bot;
+            Polled pq{};
+            if (GLB && multi && s > 0) pq = poll(e);
             cp_async_wait_all();                              // my share of r^t for this step has landed ...
             exchange_rows(0, top, bot);                       // ... and after this barrier everybody's has
             if (s + 1 < T_) fetch_rt(T_ - 2 - s, 1);          // next step's tile (its buffer was last read in step s-1)
-            if (multi && s > 0) take_refresh(e, top, bot);
+            if (multi && s > 0) take_refresh(e, pq, top, bot);
             bwd_step(std::false_type{}, top, bot, rt, 0, 0u);
             if (s + 1 >= T_) break;
             // ===== odd reverse step s+1 =====
@@ -1035,13 +1055,11 @@ fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant_
 }
 
 // ---- host side: pick the cluster shape and the tiling ----------------------------------------------------
-constexpr int kNW = 8;
+constexpr int kNW = 8;                        // warps per CTA of the one-CTA-per-SM variants
 constexpr int kPFwd = 10;                     // forward: 64 x 80 pixel register tile per CTA
 constexpr int kPBwd = 8;                      // backward: 64 x 64 (twice the per-pixel register state)
 constexpr int kHistSlots = 192;               // history scratch tiles, indexed by %smid (B200: 148 SMs; guarded in the kernel)
 
-constexpr long kMaxGlobalExchangeCtas = 512;      // upper bound on the grid of the global-memory exchange
-struct Tiling { int cx, cy, ntx, nty, stepx, stepy, ew, eh; long ctas; bool ok; };
 
 inline int tiles_needed(int extent, int size, int margin, int* step)
 {
@@ -1056,10 +1074,12 @@ inline int tiles_needed(int extent, int size, int margin, int* step)
 // What the GPU can hold at once (1 CTA per SM kernels): SM count and, per hardware cluster size, how many clusters
 // are co-resident.  Defaults = B200 as measured with tools/microbench/clusters.cu (GPCs of different sizes make
 // large clusters expensive: 7 clusters of 11-16 CTAs, 15 of 7-9, 26 of 5); refined per device at run time.
-struct Capacity { int sms; int clusters[17]; };
-inline Capacity default_capacity()
+inline Capacity default_capacity(int ctas_per_sm = 1)
 {
-    return Capacity{148, {0, 148, 74, 45, 33, 26, 22, 15, 15, 15, 11, 7, 7, 7, 7, 7, 7}};
+    Capacity c{148, {0, 148, 74, 45, 33, 26, 22, 15, 15, 15, 11, 7, 7, 7, 7, 7, 7}};
+    c.sms *= ctas_per_sm;
+    for (int i = 1; i <= 16; ++i) c.clusters[i] *= ctas_per_sm;
+    return c;
 }
 
 // th = rows of one CTA tile (kNW * P); planes = independent images (B * C).  Picks the cluster shape / tile grid that
@@ -1131,43 +1151,26 @@ bool make_guidance_map(const T* guidance, int64_t gbs, int B, int H, int W, CUte
 
 template <int TH> constexpr size_t inbox_bytes() { return (size_t)InboxGeom<TH>::size * sizeof(uint4); }
 
-// Per-device facts needed to choose the exchange transport, queried once.
-struct DeviceFacts { bool valid; int sms; int max_clusters[2][17]; bool cap_valid[2]; Capacity cap[2]; };
-inline DeviceFacts& device_facts(int dev)
-{
-    static DeviceFacts facts[64];
-    static std::mutex mu;
-    std::lock_guard<std::mutex> lock(mu);
-    DeviceFacts& f = facts[dev & 63];
-    if (!f.valid) {
-        cudaDeviceGetAttribute(&f.sms, cudaDevAttrMultiProcessorCount, dev);
-        for (int i = 0; i <= 16; ++i) f.max_clusters[0][i] = f.max_clusters[1][i] = -1;
-        f.cap_valid[0] = f.cap_valid[1] = false;
-        f.valid = true;
-    }
-    return f;
-}
-
-template <typename T, int P, int MODE, bool TMA, bool BWD>
+template <typename T, int P, int NW, int MODE, bool TMA, bool BWD>
 constexpr size_t fused_smem_bytes()
 {
-    constexpr size_t stage = TMA ? Stage<T, kNW * P, MODE>::bytes : 0;
-    constexpr size_t tiles = BWD ? BwdTiles<kNW * P>::bytes : 0;
-    return sizeof(Smem<kNW, P>) + (stage > tiles ? stage : tiles) + (BWD ? BwdTiles<kNW * P>::stash_bytes : 0);
+    constexpr size_t stage = TMA ? Stage<T, NW * P, MODE>::bytes : 0;
+    constexpr size_t tiles = BWD ? BwdTiles<NW * P>::bytes : 0;
+    return sizeof(Smem<NW, P>) + (stage > tiles ? stage : tiles) + (BWD ? BwdTiles<NW * P>::stash_bytes : 0);
 }
 
-template <typename T, int P, int MODE, bool TMA, bool GLB, bool BWD>
+template <typename T, int P, int NW, int MODE, bool TMA, bool GLB, bool BWD>
 int launch_variant(const FusedParams<T>& p, const CUtensorMap& map, const Tiling& tl, int planes, cudaStream_t stream)
 {
-    auto kern = fused3x3_kernel<T, P, kNW, MODE, TMA, GLB, BWD>;
-    constexpr size_t smem = fused_smem_bytes<T, P, MODE, TMA, BWD>();
-    static_assert(smem <= 227 * 1024, "shared memory budget of one SM exceeded");
+    auto kern = fused3x3_kernel<T, P, NW, MODE, TMA, GLB, BWD>;
+    constexpr size_t smem = fused_smem_bytes<T, P, NW, MODE, TMA, BWD>();
+    static_assert(smem * (NW <= 5 ? 2 : 1) <= 227 * 1024, "shared memory budget of one SM exceeded");
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(tl.ntx * tl.cx), (unsigned)(tl.nty * tl.cy), (unsigned)planes);
-    cfg.blockDim = dim3(kNW * 32);
+    cfg.blockDim = dim3(NW * 32);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute at[1];
@@ -1186,42 +1189,53 @@ int launch_variant(const FusedParams<T>& p, const CUtensorMap& map, const Tiling
     return 0;
 }
 
-// How many clusters of `size` CTAs can be resident at once (1 CTA per SM kernel).
-template <typename T, int P, int MODE, bool BWD>
-int max_active_clusters(int dev, int size)
-{
-    DeviceFacts& f = device_facts(dev);
-    if (f.max_clusters[BWD][size] >= 0) return f.max_clusters[BWD][size];
-    auto kern = fused3x3_kernel<T, P, kNW, MODE, true, false, BWD>;
-    constexpr size_t smem = fused_smem_bytes<T, P, MODE, true, BWD>();
-    cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)size, 1, 64); cfg.blockDim = dim3(kNW * 32); cfg.dynamicSmemBytes = smem;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = (unsigned)size; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); n = default_capacity().clusters[size]; }
-    f.max_clusters[BWD][size] = n;
-    return n;
-}
-
-// Capacity of the current device for the forward (BWD = false, P = kPFwd) or backward kernel; the B200 defaults when
-// there is no usable device (workspace queries on a machine without a GPU).
-template <int P, bool BWD>
+// What the current device holds at once for one kernel configuration: CTA slots and co-resident clusters per cluster
+// size (occupancy queries, cached per device).  The B200 defaults when there is no usable device (workspace queries
+// on a machine without a GPU).
+template <int P, int NW, bool BWD>
 Capacity capacity()
 {
+    constexpr int per_sm = NW <= 5 ? 2 : 1;
+    static Capacity cache[64];
+    static bool valid[64] = {};
+    static std::mutex mu;
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return default_capacity(); }
-    DeviceFacts& f = device_facts(dev);
-    if (f.cap_valid[BWD]) return f.cap[BWD];
-    if (f.sms <= 0) { cudaGetLastError(); return default_capacity(); }
-    Capacity c{}; c.sms = f.sms; c.clusters[0] = 0;
-    for (int size = 1; size <= 16; ++size) c.clusters[size] = max_active_clusters<float, P, CSPN_MODE_NEW, BWD>(dev, size);
-    f.cap[BWD] = c; f.cap_valid[BWD] = true;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return default_capacity(per_sm); }
+    std::lock_guard<std::mutex> lock(mu);
+    if (valid[dev & 63]) return cache[dev & 63];
+    auto kern = fused3x3_kernel<float, P, NW, CSPN_MODE_NEW, true, false, BWD>;
+    constexpr size_t smem = fused_smem_bytes<float, P, NW, CSPN_MODE_NEW, true, BWD>();
+    int sms = 0, blocks = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0 ||
+        cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kern, NW * 32, smem) != cudaSuccess || blocks <= 0) {
+        cudaGetLastError();
+        return default_capacity(per_sm);
+    }
+    Capacity c{}; c.sms = sms * blocks; c.clusters[0] = 0;
+    for (int size = 1; size <= 16; ++size) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)size, 1, 64); cfg.blockDim = dim3(NW * 32); cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)size; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); n = default_capacity(per_sm).clusters[size]; }
+        c.clusters[size] = n;
+    }
+    cache[dev & 63] = c; valid[dev & 63] = true;
     return c;
+}
+
+template <typename T>
+FusedParams<T> forward_params(const FwdArgs<T>& a)
+{
+    FusedParams<T> p{};
+    p.g = a.guidance; p.gbs = a.gbs; p.depth = a.depth; p.sparse = a.sparse; p.sparse_channels = a.sparse_channels; p.out = a.out;
+    p.C = a.C; p.H = a.H; p.W = a.W; p.iters = a.iters;
+    return p;
 }
 
 inline std::atomic<uint32_t>& exchange_epoch()
@@ -1232,10 +1246,10 @@ inline std::atomic<uint32_t>& exchange_epoch()
 
 // Common launcher: p carries the problem (pointers, sizes, tiling); inbox / inbox_bytes = optional scratch for the
 // global-memory exchange.
-template <typename T, int P, int MODE, bool BWD>
+template <typename T, int P, int NW, int MODE, bool BWD>
 int launch(FusedParams<T> p, const Tiling& tl, int B, void* inbox, size_t inbox_avail, cudaStream_t stream)
 {
-    constexpr int TH = kNW * P;
+    constexpr int TH = NW * P;
     p.cx = tl.cx; p.cy = tl.cy; p.ntx = tl.ntx; p.nty = tl.nty; p.stepx = tl.stepx; p.stepy = tl.stepy; p.ew = tl.ew; p.eh = tl.eh;
     p.margin = p.iters;
     const int planes = B * p.C;
@@ -1246,9 +1260,8 @@ int launch(FusedParams<T> p, const Tiling& tl, int B, void* inbox, size_t inbox_
     const long ctas = tl.ctas * planes;
     static const int force = [] { const char* v = getenv("CSPN_EXCHANGE"); return !v ? 0 : (!strcmp(v, "dsmem") ? 1 : (!strcmp(v, "global") ? 2 : 0)); }();   // debugging knob
     if (force != 1 && tl.cx * tl.cy > 1 && inbox && inbox_avail >= (size_t)ctas * inbox_bytes<TH>() && ctas <= kMaxGlobalExchangeCtas && p.iters <= 60) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (ctas <= device_facts(dev).sms && (force == 2 || tl.cx * tl.cy > 16 || (long)tl.ntx * tl.nty * planes > max_active_clusters<T, P, MODE, BWD>(dev, tl.cx * tl.cy))) glb = true;
+        const Capacity cap = capacity<P, NW, BWD>();
+        if (ctas <= cap.sms && (force == 2 || tl.cx * tl.cy > 16 || (long)tl.ntx * tl.nty * planes > cap.clusters[tl.cx * tl.cy])) glb = true;
     }
     if (!glb && tl.cx * tl.cy > 16) return CSPN_ERR_WORKSPACE;      // this tiling only exists for the global-memory exchange
     if (glb) {
@@ -1258,8 +1271,8 @@ int launch(FusedParams<T> p, const Tiling& tl, int B, void* inbox, size_t inbox_
     alignas(64) CUtensorMap map;
     memset(&map, 0, sizeof map);
     const bool tma = make_guidance_map<T, TH, MODE>(p.g, p.gbs, B, p.H, p.W, &map);      // false: unaligned guidance, plain-load prologue
-    if (glb) return tma ? launch_variant<T, P, MODE, true, true, BWD>(p, map, tl, planes, stream) : launch_variant<T, P, MODE, false, true, BWD>(p, map, tl, planes, stream);
-    return tma ? launch_variant<T, P, MODE, true, false, BWD>(p, map, tl, planes, stream) : launch_variant<T, P, MODE, false, false, BWD>(p, map, tl, planes, stream);
+    if (glb) return tma ? launch_variant<T, P, NW, MODE, true, true, BWD>(p, map, tl, planes, stream) : launch_variant<T, P, NW, MODE, false, true, BWD>(p, map, tl, planes, stream);
+    return tma ? launch_variant<T, P, NW, MODE, true, false, BWD>(p, map, tl, planes, stream) : launch_variant<T, P, NW, MODE, false, false, BWD>(p, map, tl, planes, stream);
 }
 
 }  // namespace
