@@ -30,7 +30,7 @@ SIGNATURES = {
     "cspn_fwd_host_f16": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_int, _c_vp] + [_c_int] * 7 + [_c_vp]),
 }
 
-PATH_AUTO, PATH_GENERIC, PATH_FUSED = 0, 1, 2
+PATH_AUTO, PATH_GENERIC, PATH_FUSED, PATH_BLOCKED = 0, 1, 2, 3
 MODE_NEW, MODE_OURS = 0, 1
 
 _lock = threading.Lock()

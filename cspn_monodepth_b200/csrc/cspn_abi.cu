@@ -45,6 +45,11 @@ bool use_fused(int C, int H, int W, int iters, int ksize, int mode, int* err)
     return path != CSPN_PATH_GENERIC && ok;
 }
 
+bool use_blocked(int B, int C, int H, int W, int iters, int ksize, int mode)
+{
+    return g_path.load(std::memory_order_relaxed) == CSPN_PATH_AUTO && blocked5x5_supported(B, C, H, W, iters, ksize, mode);
+}
+
 bool use_fused_bwd(int C, int H, int W, int iters, int ksize, int mode, int* err)
 {
     const int path = g_path.load(std::memory_order_relaxed);
@@ -74,6 +79,11 @@ int forward_impl(const T* guidance, int64_t gbs, const T* depth, const T* sparse
         return rc;
     }
     if (err != CSPN_OK) return err;
+    if (iters > 0 && use_blocked(B, C, H, W, iters, ksize, mode)) {
+        rc = blocked5x5_forward<T>(a);
+        if (rc == CSPN_OK) call_stats().path = CSPN_PATH_BLOCKED;
+        return rc;
+    }
     if (iters > 0) {
         const size_t need = generic_fwd_workspace(B, C, H, W, tt.n);
         if (!ws || ws_bytes < need) return CSPN_ERR_WORKSPACE;
@@ -194,6 +204,7 @@ size_t cspn_fwd_workspace_bytes(int B, int C, int H, int W, int iters, int ksize
     TapTable tt;
     if (!make_taps(mode, ksize, &tt) || B < 1 || C < 1 || H < 1 || W < 1 || iters < 1) return 0;
     if (use_fused(C, H, W, iters, ksize, mode, nullptr)) return fused_workspace(B, C, H, W, iters);
+    if (use_blocked(B, C, H, W, iters, ksize, mode)) return blocked5x5_workspace(B, C, H, W, iters);
     return generic_fwd_workspace(B, C, H, W, tt.n);
 }
 

@@ -91,6 +91,11 @@ bool fused_supported(int C, int H, int W, int iters, int ksize, int mode);
 template <typename T> int fused_forward(const FwdArgs<T>& a);
 size_t fused_workspace(int B, int C, int H, int W, int iters);   // optional scratch (0 = none)
 
+// temporally blocked forward for the 5x5 variant (cspn_blocked5x5.cu): 4 steps per launch, weights in registers
+bool blocked5x5_supported(int B, int C, int H, int W, int iters, int ksize, int mode);
+template <typename T> int blocked5x5_forward(const FwdArgs<T>& a);
+size_t blocked5x5_workspace(int B, int C, int H, int W, int iters);
+
 // fused backward (cspn_fused3x3_bwd.cu): recompute + reverse sweep + Jacobians in one launch, 3x3, one depth channel
 bool fused_bwd_supported(int C, int H, int W, int iters, int ksize, int mode);
 template <typename T> int fused_backward(const BwdArgs<T>& a);

@@ -1057,7 +1057,11 @@ fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant_
 // ---- host side: pick the cluster shape and the tiling ----------------------------------------------------
 constexpr int kNW = 8;                        // warps per CTA of the one-CTA-per-SM variants
 constexpr int kPFwd = 10;                     // forward: 64 x 80 pixel register tile per CTA
-constexpr int kPBwd = 8;                      // backward: 64 x 64 (twice the per-pixel register state)
+#ifndef CSPN_BWD_WARPS
+#define CSPN_BWD_WARPS 8
+#endif
+constexpr int kNWBwd = CSPN_BWD_WARPS;        // backward: 64 x 64 tile (twice the per-pixel register state of the forward);
+constexpr int kPBwd = 64 / kNWBwd;            //           8 warps x 8 rows (16 warps x 4 rows at 128 registers measured the same)
 constexpr int kHistSlots = 192;               // history scratch tiles, indexed by %smid (B200: 148 SMs; guarded in the kernel)
 
 

@@ -6,7 +6,7 @@
 namespace cspn {
 
 namespace {
-constexpr int kTHBwd = kNW * kPBwd;
+constexpr int kTHBwd = kNWBwd * kPBwd;
 inline size_t up256(size_t v) { return (v + 255) & ~(size_t)255; }
 inline size_t hist_bytes(int iters) { return (size_t)kHistSlots * (size_t)iters * kTHBwd * kTileW * sizeof(float); }
 inline size_t bwd_inbox_bytes(const Tiling& tl, int B)
@@ -29,7 +29,7 @@ bool fused_bwd_supported(int C, int H, int W, int iters, int ksize, int mode)
 size_t fused_bwd_workspace(int B, int C, int H, int W, int iters)
 {
     (void)C;
-    const Tiling tl = choose_tiling(H, W, iters, kTHBwd, (long)B, capacity<kPBwd, kNW, true>());
+    const Tiling tl = choose_tiling(H, W, iters, kTHBwd, (long)B, capacity<kPBwd, kNWBwd, true>());
     if (!tl.ok) return 0;
     return bwd_inbox_bytes(tl, B) + hist_bytes(iters);
 }
@@ -37,7 +37,7 @@ size_t fused_bwd_workspace(int B, int C, int H, int W, int iters)
 template <typename T>
 int fused_backward(const BwdArgs<T>& a)
 {
-    const Tiling tl = choose_tiling(a.H, a.W, a.iters, kTHBwd, (long)a.B, capacity<kPBwd, kNW, true>());
+    const Tiling tl = choose_tiling(a.H, a.W, a.iters, kTHBwd, (long)a.B, capacity<kPBwd, kNWBwd, true>());
     if (!tl.ok || a.C != 1) return CSPN_ERR_BAD_KERNEL_SIZE;
     if ((long)a.B > 65535) return CSPN_ERR_BAD_SHAPE;
     const size_t inbox = bwd_inbox_bytes(tl, a.B);
@@ -53,8 +53,8 @@ int fused_backward(const BwdArgs<T>& a)
     p.C = 1; p.H = a.H; p.W = a.W; p.iters = a.iters;
     p.gout = a.grad_out; p.gg = a.grad_guidance; p.gd = a.grad_depth; p.Cg = a.Cg;
     p.hist = (float*)((char*)a.ws + inbox); p.hist_slots = kHistSlots;
-    return a.mode == CSPN_MODE_NEW ? launch<T, kPBwd, kNW, CSPN_MODE_NEW, true>(p, tl, a.B, inbox ? a.ws : nullptr, inbox, a.stream)
-                                   : launch<T, kPBwd, kNW, CSPN_MODE_OURS, true>(p, tl, a.B, inbox ? a.ws : nullptr, inbox, a.stream);
+    return a.mode == CSPN_MODE_NEW ? launch<T, kPBwd, kNWBwd, CSPN_MODE_NEW, true>(p, tl, a.B, inbox ? a.ws : nullptr, inbox, a.stream)
+                                   : launch<T, kPBwd, kNWBwd, CSPN_MODE_OURS, true>(p, tl, a.B, inbox ? a.ws : nullptr, inbox, a.stream);
 }
 
 template int fused_backward<float>(const BwdArgs<float>&);

@@ -77,13 +77,14 @@ extern "C" {
 #define CSPN_PATH_AUTO 0    /* fused single-launch kernel whenever the configuration is supported */
 #define CSPN_PATH_GENERIC 1 /* one launch per iteration (any K, any shape); for debugging and A/B timing */
 #define CSPN_PATH_FUSED 2   /* fused kernel or CSPN_ERR_BAD_KERNEL_SIZE if unsupported */
+#define CSPN_PATH_BLOCKED 3 /* reported by cspn_last_path only: temporally blocked 5x5 forward (4 steps per launch), chosen by AUTO */
 
 CSPN_API int cspn_abi_version(void);
 CSPN_API const char* cspn_error_string(int code);
 
 /* Process-wide override of the forward path, mainly for tests and benchmarks. Returns the previous value. */
 CSPN_API int cspn_set_path(int path);
-/* Which path the last successful cspn_fwd_* call on this host thread took (CSPN_PATH_GENERIC or CSPN_PATH_FUSED). */
+/* Which path the last successful cspn_fwd_* / cspn_bwd_* call on this host thread took (CSPN_PATH_GENERIC, _FUSED or _BLOCKED). */
 CSPN_API int cspn_last_path(void);
 /* Number of kernel launches enqueued by the last successful call on this host thread. */
 CSPN_API int cspn_last_launch_count(void);

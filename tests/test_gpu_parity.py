@@ -130,13 +130,43 @@ def test_iteration_counts(path, iters):
     assert_close_nan(y.cpu().numpy(), _oracle(("it-ns", iters), g, d, None, iters, 3, 0), FWD_ATOL, f"T={iters} no sparse")
 
 
-def test_five_by_five_pac_variant():
+@pytest.mark.parametrize("path", PATHS)
+def test_five_by_five_pac_variant(path):
+    _lib.load().cspn_set_path(path)
     g, d, s = make_inputs(55, 2, 24, 1, 60, 80, density=0.02)           # cfg4 shape family: K=5, T=12
     y, _, _ = _run(1, g, d, s, 12)
+    assert _lib.load().cspn_last_path() == (_lib.PATH_GENERIC if path == _lib.PATH_GENERIC else _lib.PATH_BLOCKED)
     assert_close_nan(y.cpu().numpy(), c_oracle.forward(g, d, s, 12, 5, 1), FWD_ATOL, "5x5")
     g, d, s = make_inputs(77, 1, 48, 1, 20, 30, density=0.02)
     y, _, _ = _run(1, g, d, s, 4)
     assert_close_nan(y.cpu().numpy(), c_oracle.forward(g, d, s, 4, 7, 1), FWD_ATOL, "7x7")
+
+
+# The temporally blocked 5x5 kernel (4 steps per launch, trapezoid tiles): ragged shapes, widths that are not a
+# multiple of 4 (scalar loads), every launch count (T = 1..13), no sparse, negative sparse, fp16, several channels.
+@pytest.mark.parametrize("shape", [(2, 480, 640), (1, 100, 52), (3, 33, 47), (1, 7, 203), (2, 130, 9)])
+def test_blocked_5x5_shape_grid(shape):
+    b, h, w = shape
+    g, d, s = make_inputs(h * w, b, 24, 1, h, w, density=0.02)
+    y, _, _ = _run(1, g, d, s, 12)
+    assert _lib.load().cspn_last_path() == _lib.PATH_BLOCKED and _lib.load().cspn_last_launch_count() == 3
+    assert_close_nan(y.cpu().numpy(), c_oracle.forward(g, d, s, 12, 5, 1, threads=0), FWD_ATOL, f"5x5 {shape}")
+
+
+@pytest.mark.parametrize("iters", [1, 3, 4, 5, 8, 9, 13])
+def test_blocked_5x5_iteration_counts_and_variants(iters):
+    g, d, s = make_inputs(500 + iters, 2, 24, 2, 70, 96, density=0.05, neg=iters == 5, sparse_channels=2 if iters % 2 else 1)
+    y, _, _ = _run(1, g, d, s, iters)
+    assert _lib.load().cspn_last_launch_count() == (iters + 3) // 4
+    ref = c_oracle.forward(g, d, s, iters, 5, 1)
+    assert_close_nan(y.cpu().numpy(), ref, _atol(ref), f"5x5 T={iters}")
+    y, _, _ = _run(1, g, d, None, iters)
+    assert_close_nan(y.cpu().numpy(), c_oracle.forward(g, d, None, iters, 5, 1), FWD_ATOL, f"5x5 T={iters} no sparse")
+    g16, d16, s16 = (a.astype(np.float16) for a in (g, d, s))
+    y, _, _ = _run(1, g16, d16, s16, iters, dtype=torch.float16)
+    ref = c_oracle.forward(g16.astype(np.float32), d16.astype(np.float32), s16.astype(np.float32), iters, 5, 1)
+    err = np.abs(y.float().cpu().numpy() - ref)
+    assert (err <= np.abs(ref) * 2.0 ** -10 + _atol(ref)).all(), f"5x5 fp16 T={iters}: max err {err.max():.3e}"
 
 
 @pytest.mark.parametrize("path", PATHS)
