@@ -250,6 +250,50 @@ def time_e2e(cfg, dev, steps):
     return e0.elapsed_time(e1) / steps, h2d, d2h, float(outs[0].float().mean())
 
 
+def time_fwd_bwd(cfg, dev, steps):
+    """Forward + backward of one batch through the raw C ABI (cspn_fwd_* then cspn_bwd_*), graph-replayed, rotating inputs.
+    Returns (ms per step, kernel launches per step)."""
+    from cspn_monodepth_b200 import _lib
+    lib = _lib.load()
+    b, h, w, it, k, mode = cfg["B"], cfg["H"], cfg["W"], cfg["iters"], cfg["ksize"], cfg["mode"]
+    cg = k * k - 1
+    sfx = cfg["dtype"]
+    px_bytes = BYTES_PER_PX[(cfg["dtype"], k)] * b * h * w
+    nsets = max(2, int(np.ceil(1.5 * L2_BYTES / px_bytes)))
+    sets = [[t.to(dev) for t in synth(cfg, 300 + i)] for i in range(nsets)]
+    gout = torch.randn_like(sets[0][1])
+    out, gg, gd = torch.empty_like(sets[0][1]), torch.empty_like(sets[0][0]), torch.empty_like(sets[0][1])
+    nf, nb = lib.cspn_fwd_workspace_bytes(b, 1, h, w, it, k, mode), lib.cspn_bwd_workspace_bytes(b, 1, h, w, it, k, mode)
+    wsf = torch.empty(max(nf, 16), dtype=torch.uint8, device=dev)
+    wsb = torch.empty(max(nb, 16), dtype=torch.uint8, device=dev)
+    fwd_fn, bwd_fn = getattr(lib, "cspn_fwd_" + sfx), getattr(lib, "cspn_bwd_" + sfx)
+    launches = [0]
+
+    def step(i):
+        g, d, s = sets[i % nsets]
+        stream = torch.cuda.current_stream().cuda_stream
+        _lib.check(fwd_fn(g.data_ptr(), cg * h * w, d.data_ptr(), s.data_ptr(), 1, out.data_ptr(), b, 1, h, w, it, k, mode, wsf.data_ptr(), nf, stream))
+        n = lib.cspn_last_launch_count()
+        _lib.check(bwd_fn(gout.data_ptr(), g.data_ptr(), cg * h * w, cg, d.data_ptr(), s.data_ptr(), 1, gg.data_ptr(), gd.data_ptr(),
+                          b, 1, h, w, it, k, mode, wsb.data_ptr(), nb, stream))
+        launches[0] = n + lib.cspn_last_launch_count()
+    for i in range(3):
+        step(i)
+    torch.cuda.synchronize(dev)
+    side = torch.cuda.Stream(dev)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            for i in range(steps):
+                step(i)
+    graph.replay()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); graph.replay(); e1.record()
+    torch.cuda.synchronize(dev)
+    return e0.elapsed_time(e1) / steps, launches[0]
+
+
 def cpu_reference(cfg, min_seconds=4.0, max_steps=8, batch=None):
     """Reference CPU path (op-for-op port) on a bounded sample; returns dict for `cpu_baseline`."""
     from oracle import torch_port
@@ -362,6 +406,17 @@ def main():
                     extra[name] = {"value": px / (ms / st * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms / st, "launches_per_step": ln,
                                    "roofline_frac": gbs / peak, "input_sets": ns}
                 except Exception as exc:        # context numbers must not take the headline down
+                    extra[name] = {"error": repr(exc)[:200]}
+                torch.cuda.empty_cache()
+            # forward + backward (BASELINE.json configs[2] is forward+backward): algorithmic bytes 11 + 20 elements per pixel
+            for name, c, st in (("kitti_b32_1216x352_f16_fwd_bwd", KITTI, 10), ("nyu_b8_304x228_f32_fwd_bwd", NYU, 100)):
+                try:
+                    ms, ln = time_fwd_bwd(c, dev, st)
+                    px = c["B"] * c["H"] * c["W"]
+                    es = 4 if c["dtype"] == "f32" else 2
+                    extra[name] = {"value": px / (ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms, "launches_per_step": ln,
+                                   "roofline_frac": 31 * es * px / (ms * 1e-3) / 1e9 / peak}
+                except Exception as exc:
                     extra[name] = {"error": repr(exc)[:200]}
                 torch.cuda.empty_cache()
             line["extra"] = extra

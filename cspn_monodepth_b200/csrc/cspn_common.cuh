@@ -81,9 +81,10 @@ template <typename T> int generic_forward(const FwdArgs<T>& a, const TapTable& t
 template <typename T> int generic_backward(const BwdArgs<T>& a, const TapTable& tt);
 
 // ---- fused path: whole recurrence in one launch, 3x3 only (cspn_fused3x3*.cu) -------------------------------
-constexpr long kMaxGlobalExchangeCtas = 512;      // upper bound on the grid of the global-memory halo exchange
-// Cluster shape (cx x cy CTAs) and grid of cluster tiles (ntx x nty per image) covering an image.
-struct Tiling { int cx, cy, ntx, nty, stepx, stepy, ew, eh; long ctas; bool ok; };
+constexpr long kMaxGlobalExchangeCtas = 1l << 20;  // upper bound on the tiles of a streamed problem (one inbox each)
+// Cluster shape (cx x cy CTAs) and grid of cluster tiles (ntx x nty per image) covering an image.  stream: the image is
+// one virtual cluster walked by a persistent grid with the halo exchange in global memory (no hardware cluster).
+struct Tiling { int cx, cy, ntx, nty, stepx, stepy, ew, eh; long ctas; bool ok; bool stream; };
 // What the GPU holds at once for one kernel configuration: sms = CTA slots of the whole GPU (SMs x resident CTAs per
 // SM), clusters[n] = co-resident hardware clusters of n CTAs.
 struct Capacity { int sms; int clusters[17]; };

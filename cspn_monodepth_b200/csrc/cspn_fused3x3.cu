@@ -32,9 +32,8 @@ bool fused_supported(int C, int H, int W, int iters, int ksize, int mode)
 size_t fused_workspace(int B, int C, int H, int W, int iters)
 {
     const Tiling tl = plan_forward(B, C, H, W, iters);
-    if (!tl.ok || tl.cx * tl.cy == 1) return 0;
-    const long ctas = tl.ctas * (long)B * C;
-    return ctas <= kMaxGlobalExchangeCtas ? (size_t)ctas * inbox_bytes<kTHBig>() : 0;     // inboxes of the global-memory exchange
+    if (!tl.ok || !tl.stream) return 0;
+    return (size_t)(tl.ctas * (long)B * C) * inbox_bytes<kTHBig>();     // inboxes of the global-memory exchange, one per tile
 }
 
 template <typename T>

@@ -198,7 +198,8 @@ struct FusedParams {
     int stepx, stepy;     // origin spacing of cluster tiles
     int ew, eh;           // extent of one cluster tile
     int margin;           // decaying halo at cluster-tile edges that are not image borders (= iters)
-    uint4* inbox;         // GLB exchange only: one Inbox per CTA in global memory
+    uint32_t total_tiles; // GLB exchange only: cx * cy * planes tiles, processed by a persistent grid
+    uint4* inbox;         // GLB exchange only: one Inbox per CTA tile in global memory
     uint32_t tag_base;    // GLB exchange only: tag of refresh e is tag_base + e
     // backward only
     const T* gout;        // dL/d out
@@ -269,14 +270,16 @@ template <int TH> struct BwdTiles {
     static constexpr size_t stash_bytes = (size_t)TH * kTileW * sizeof(float) + (size_t)TH * 32 * sizeof(uint32_t);
 };
 
+// One CTA tile from prologue to epilogue.  (bx, by, bz) = position of the tile in the (gdx, gdy, planes) grid of CTA
+// tiles - the launch grid itself for hardware clusters, the tile counter of the persistent loop for the global-memory
+// exchange; use = how many tiles this CTA has processed before (phase parity of the re-used TMA barriers).
 template <typename T, int P, int NW, int MODE, bool TMA, bool GLB, bool BWD>
-__global__ void __launch_bounds__(NW * 32, (NW <= 5 ? 2 : 1))
-fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant__ CUtensorMap gmap)
+__device__ __forceinline__ void fused_tile(const FusedParams<T>& p, const CUtensorMap* gmap, unsigned char* smem_raw,
+                                           const uint32_t bx, const uint32_t by, const uint32_t bz, const uint32_t gdx, const uint32_t gdy, const uint32_t use)
 {
     constexpr int TH = NW * P;
     constexpr int STEPY = TH - 2 * kHaloY;
     using St = Stage<T, TH, MODE>;
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
     Smem<NW, P>& sm = *reinterpret_cast<Smem<NW, P>*>(smem_raw);
     const T* stage = reinterpret_cast<const T*>(smem_raw + sizeof(Smem<NW, P>));
     constexpr size_t kStashOff = sizeof(Smem<NW, P>) + ((TMA ? St::bytes : 0) > BwdTiles<TH>::bytes ? (TMA ? St::bytes : 0) : BwdTiles<TH>::bytes);
@@ -286,9 +289,9 @@ fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant_
     TRACE(0);
     const bool multi = p.cx * p.cy > 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int ccx = blockIdx.x % p.cx, ccy = blockIdx.y % p.cy;
-    const int tix = blockIdx.x / p.cx, tiy = blockIdx.y / p.cy;
-    const int plane = blockIdx.z, b = plane / p.C, ch = plane - b * p.C;
+    const int ccx = bx % p.cx, ccy = by % p.cy;
+    const int tix = bx / p.cx, tiy = by / p.cy;
+    const int plane = bz, b = plane / p.C, ch = plane - b * p.C;
     const bool has_left = ccx > 0, has_right = ccx < p.cx - 1, has_up = ccy > 0, has_down = ccy < p.cy - 1;
     const int H = p.H, W = p.W;
     const size_t hw = (size_t)H * W;
@@ -298,28 +301,18 @@ fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant_
     const int gx = ox + 2 * lane;
     const int gy0 = oy + warp * P;
 
-    // ---- barriers + TMA issue (one thread) --------------------------------------------------------------
-    if (threadIdx.x == 0) {
-        mbar_init(smem_u32(&sm.halo_bar[0]), 1);
-        mbar_init(smem_u32(&sm.halo_bar[1]), 1);
+    // ---- TMA issue (one thread): 8 boxes, one per guidance channel, each on its own barrier --------------------
+    if (TMA && threadIdx.x == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 #pragma unroll
-        for (int k = 0; k < 8; ++k) mbar_init(smem_u32(&sm.tma_bar[k]), 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if (TMA) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const uint32_t bar = smem_u32(&sm.tma_bar[k]);
-                mbar_arrive_expect_tx(bar, (uint32_t)St::box_bytes);
-                tma_load_4d(smem_u32(stage + (size_t)k * St::plane), &gmap, bar, St::box_x(ox), oy - St::apron, k, b);
-            }
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t bar = smem_u32(&sm.tma_bar[k]);
+            mbar_arrive_expect_tx(bar, (uint32_t)St::box_bytes);
+            tma_load_4d(smem_u32(stage + (size_t)k * St::plane), gmap, bar, St::box_x(ox), oy - St::apron, k, b);
         }
     }
     TRACE(1);
-    __syncthreads();
-    // "my barriers exist": neighbours may only push into this CTA after everyone passed the matching wait
     const bool hw_cluster = multi && !GLB;
-    if (hw_cluster) cluster_arrive();
 
     const T* db = p.depth + (size_t)plane * hw;
     const T* sb = p.sparse ? p.sparse + ((size_t)b * p.sparse_channels + (p.sparse_channels == 1 ? 0 : ch)) * hw : nullptr;
@@ -378,7 +371,7 @@ fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant_
         const int x_off = ox - St::box_x(ox);           // column of the tile's first pixel inside the staged box
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            mbar_wait(smem_u32(&sm.tma_bar[k]), 0);
+            mbar_wait(smem_u32(&sm.tma_bar[k]), use & 1u);
             TRACE(3 + k);
             const T* sp = stage + (size_t)k * St::plane;
             if (MODE == CSPN_MODE_NEW) {
@@ -526,7 +519,7 @@ fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant_
         if (side >= 0) {
             msg_src = (uint32_t)(side * TH + srow) * 8u;
             if (GLB) {
-                const uint32_t nblk = (blockIdx.z * gridDim.y + blockIdx.y + dcy) * gridDim.x + blockIdx.x + (side == 0 ? -1 : 1);
+                const uint32_t nblk = (bz * gdy + by + dcy) * gdx + bx + (side == 0 ? -1 : 1);
                 msg_dst = nblk * IG::size + (side == 0 ? IG::col_side : 0u) + (uint32_t)drow;   // uint4 index, parity 0; never 0
             } else {
                 const uint32_t nb = mapa(sm_base, my_rank + dcy * p.cx + (side == 0 ? -1 : 1));
@@ -535,7 +528,7 @@ fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant_
             }
         }
     }
-    const uint32_t my_blk = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    const uint32_t my_blk = (bz * gdy + by) * gdx + bx;
 
     auto exchange_rows = [&](int par, u64& top, u64& bot) {
         // publish this warp's edge rows for the warps above / below (same CTA), fetch theirs
@@ -564,7 +557,7 @@ fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant_
         if (has_up && warp == 0) {                                                   // warp-uniform
             // my tile rows kHaloY .. 2*kHaloY-1 are the upper neighbour's bottom halo rows
             if (GLB) {
-                uint4* d = p.inbox + (size_t)(my_blk - gridDim.x) * IG::size + IG::row_base + rpar * IG::row_par + IG::row_side + lane;
+                uint4* d = p.inbox + (size_t)(my_blk - gdx) * IG::size + IG::row_base + rpar * IG::row_par + IG::row_side + lane;
 #pragma unroll
                 for (int h = 0; h < kHaloY; ++h) st_ll(d + h * 32, A[kHaloY + h], tag);
             } else {
@@ -576,7 +569,7 @@ fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant_
         }
         if (has_down && warp == NW - 1) {
             if (GLB) {
-                uint4* d = p.inbox + (size_t)(my_blk + gridDim.x) * IG::size + IG::row_base + rpar * IG::row_par + lane;
+                uint4* d = p.inbox + (size_t)(my_blk + gdx) * IG::size + IG::row_base + rpar * IG::row_par + lane;
 #pragma unroll
                 for (int h = 0; h < kHaloY; ++h) st_ll(d + h * 32, A[P - 2 * kHaloY + h], tag);
             } else {
@@ -663,10 +656,10 @@ fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant_
             const uint32_t tag = p.tag_base + (uint32_t)e;
             const int sd = poll_sd, row = poll_row;
             const bool want = poll_want, wr0 = poll_r0, wr1 = poll_r1;
-            for (int spin = 0;; ++spin) {
+            for (int spin = 0; !poisoned; ++spin) {
                 const bool ok = q.c.y == tag && q.c.w == tag && q.r0.y == tag && q.r0.w == tag && q.r1.y == tag && q.r1.w == tag;
                 if (__all_sync(0xffffffffu, ok)) break;
-                if (spin > (1 << 22)) { poisoned = true; break; }     // neighbours never showed up (grid not co-resident?): fail loudly, do not hang
+                if (spin > (1 << 21)) { poisoned = true; break; }     // neighbours never showed up (grid not co-resident?): fail loudly, do not hang
                 q = poll(e);
             }
             const uint4 c = q.c, r0 = q.r0, r1 = q.r1;
@@ -1054,6 +1047,43 @@ fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant_
     TRACE(15);
 }
 
+// The kernel.  Hardware clusters (GLB = false): one CTA tile per CTA, grid = (cluster tiles x cluster shape, planes).
+// Global-memory exchange (GLB = true): a persistent 1-D grid of at most one CTA per SM slot under a cooperative launch
+// (all co-resident); CTA c works through tiles c, c + grid, c + 2 grid, ... of the linear order (plane, tile row, tile
+// column).  Every image is ONE virtual cluster of cx x cy tiles - no hardware limit of 16, no decaying margins - and
+// tiles only ever wait for tiles of their own image at most cx + 1 positions away: with more CTAs than that, the
+// CTA owning a larger-numbered neighbour is at worst busy with a tile that precedes every tile waiting for it, so
+// the wavefront always advances (the spin in take_refresh is bounded regardless).
+template <typename T, int P, int NW, int MODE, bool TMA, bool GLB, bool BWD>
+__global__ void __launch_bounds__(NW * 32, (NW <= 5 ? 2 : 1))
+fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant__ CUtensorMap gmap)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    Smem<NW, P>& sm = *reinterpret_cast<Smem<NW, P>*>(smem_raw);
+    if (threadIdx.x == 0) {
+        mbar_init(smem_u32(&sm.halo_bar[0]), 1);
+        mbar_init(smem_u32(&sm.halo_bar[1]), 1);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) mbar_init(smem_u32(&sm.tma_bar[k]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (!GLB) {
+        // "my barriers exist": neighbours may only push into this CTA after everyone passed the matching wait
+        if (p.cx * p.cy > 1) cluster_arrive();
+        fused_tile<T, P, NW, MODE, TMA, GLB, BWD>(p, &gmap, smem_raw, blockIdx.x, blockIdx.y, blockIdx.z, gridDim.x, gridDim.y, 0u);
+    } else {
+        const uint32_t per_image = (uint32_t)(p.cx * p.cy);
+        uint32_t use = 0u;
+        for (uint32_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++use) {
+            if (use) __syncthreads();                     // the previous tile's shared memory is dead in every warp
+            const uint32_t in_image = tile % per_image;
+            fused_tile<T, P, NW, MODE, TMA, GLB, BWD>(p, &gmap, smem_raw, in_image % (uint32_t)p.cx, in_image / (uint32_t)p.cx, tile / per_image,
+                                                      (uint32_t)p.cx, (uint32_t)p.cy, use);
+        }
+    }
+}
+
 // ---- host side: pick the cluster shape and the tiling ----------------------------------------------------
 constexpr int kNW = 8;                        // warps per CTA of the one-CTA-per-SM variants
 constexpr int kPFwd = 10;                     // forward: 64 x 80 pixel register tile per CTA
@@ -1086,37 +1116,66 @@ inline Capacity default_capacity(int ctas_per_sm = 1)
     return c;
 }
 
-// th = rows of one CTA tile (kNW * P); planes = independent images (B * C).  Picks the cluster shape / tile grid that
-// needs the fewest waves: CTAs / (CTAs the GPU holds at once for that cluster size).  A grid that fits on the GPU in
-// one piece does not need hardware clusters at all (global-memory halo exchange under a cooperative launch), so
-// there the cluster may have any shape up to the whole image and the fewest CTAs win.
+inline int exchange_override()
+{
+    static const int force = [] { const char* v = getenv("CSPN_EXCHANGE"); return !v ? 0 : (!strcmp(v, "dsmem") ? 1 : (!strcmp(v, "global") ? 2 : 0)); }();   // debugging knob
+    return force;
+}
+
+// th = rows of one CTA tile (NW * P); planes = independent images (B * C).  Two ways to run a problem:
+//  * hardware clusters (DSMEM halo exchange, ~0.75 of the tile time of the other way): cluster tiles of cx x cy <= 16
+//    CTAs with decaying margins between them; time ~ ceil(clusters / co-resident clusters of that size);
+//  * stream (tl.stream): every image is one virtual cluster of cx x cy tiles without margins, halo exchange through
+//    global memory, a persistent grid of one CTA per SM slot walks the tiles as a wavefront; time ~ tiles / slots.
 inline Tiling choose_tiling(int H, int W, int iters, int th, long planes, const Capacity& cap)
 {
     const int step_y = th - 2 * kHaloY;
-    Tiling best{}; best.ok = false; best.ctas = 0;
+    Tiling best{}; best.ok = false; best.ctas = 0; best.stream = false;
     double best_cost = 0.0;
-    for (int cx = 1; cx <= 16; ++cx)
-        for (int cy = 1; cy <= 16; ++cy) {
-            Tiling t{}; t.cx = cx; t.cy = cy;
-            t.ew = kStepX * (cx - 1) + kTileW; t.eh = step_y * (cy - 1) + th;
-            t.ntx = tiles_needed(t.ew, W, iters, &t.stepx);
-            t.nty = tiles_needed(t.eh, H, iters, &t.stepy);
-            if (t.ntx < 0 || t.nty < 0) continue;
-            if ((t.stepx & 1) != 0) continue;             // keep pixel pairs at even x
-            t.ctas = (long)t.ntx * t.nty * cx * cy; t.ok = true;
-            const long total = t.ctas * planes;
-            const bool one_piece = cx * cy > 1 && total <= cap.sms && total <= kMaxGlobalExchangeCtas;
-            if (cx * cy > 16 && !one_piece) continue;     // hardware clusters hold at most 16 CTAs
-            const long held = one_piece ? cap.sms : (long)cap.clusters[cx * cy] * cx * cy;
-            if (held <= 0) continue;
-            double cost = (double)total / (double)held;
-            if (cost < 1.0) cost = 1.0;
-            // fewest waves win; ties go to fewer CTAs, then to the smaller cluster (cheaper to place)
-            if (!best.ok || cost < best_cost - 1e-9 ||
-                (cost < best_cost + 1e-9 && (t.ctas < best.ctas || (t.ctas == best.ctas && cx * cy < best.cx * best.cy)))) {
-                best = t; best_cost = cost;
-            }
+    auto consider = [&](const Tiling& t, double cost) {
+        // cheapest wins; ties go to fewer CTAs, then to the smaller cluster (cheaper to place)
+        if (!best.ok || cost < best_cost - 1e-9 ||
+            (cost < best_cost + 1e-9 && (t.ctas < best.ctas || (t.ctas == best.ctas && t.cx * t.cy < best.cx * best.cy)))) {
+            best = t; best_cost = cost;
         }
+    };
+    {
+        for (int cx = 1; cx <= 16; ++cx)
+            for (int cy = 1; cx * cy <= 16; ++cy) {
+                Tiling t{}; t.cx = cx; t.cy = cy; t.stream = false;
+                t.ew = kStepX * (cx - 1) + kTileW; t.eh = step_y * (cy - 1) + th;
+                t.ntx = tiles_needed(t.ew, W, iters, &t.stepx);
+                t.nty = tiles_needed(t.eh, H, iters, &t.stepy);
+                if (t.ntx < 0 || t.nty < 0) continue;
+                if ((t.stepx & 1) != 0) continue;             // keep pixel pairs at even x
+                t.ctas = (long)t.ntx * t.nty * cx * cy; t.ok = true;
+                const long held = cap.clusters[cx * cy];
+                if (held <= 0) continue;
+                const long clusters = (long)t.ntx * t.nty * planes;
+                consider(t, 0.75 * (double)((clusters + held - 1) / held));
+            }
+    }
+    if (exchange_override() != 1 && iters <= 60) {
+        Tiling t{}; t.stream = true; t.ntx = t.nty = 1;
+        t.cx = W <= kTileW ? 1 : (W - kTileW + kStepX - 1) / kStepX + 1;
+        t.cy = H <= th ? 1 : (H - th + step_y - 1) / step_y + 1;
+        t.ew = kStepX * (t.cx - 1) + kTileW; t.eh = step_y * (t.cy - 1) + th;
+        t.stepx = t.ew; t.stepy = t.eh;
+        t.ctas = (long)t.cx * t.cy; t.ok = true;
+        const long total = t.ctas * planes;
+        const long grid = total < cap.sms ? total : cap.sms;
+        if (t.cx * t.cy > 1 && t.cx + 1 < grid && total <= kMaxGlobalExchangeCtas) {
+            // All tiles of an image advance in lockstep, so the grid effectively works on floor(slots / tiles per image)
+            // images at a time (measured: 32 KITTI images of 105 tiles take 32 tile times on 148 SMs); an image larger
+            // than the GPU is walked as a wavefront with stalls at the round boundaries.
+            const long per_image = t.ctas;
+            double cost;
+            if (per_image <= cap.sms) { const long groups = cap.sms / per_image; cost = (double)((planes + groups - 1) / groups); }
+            else cost = 1.5 * (double)total / (double)cap.sms;
+            if (exchange_override() == 2) cost = 0.0;
+            consider(t, cost);
+        }
+    }
     return best;
 }
 
@@ -1164,7 +1223,7 @@ constexpr size_t fused_smem_bytes()
 }
 
 template <typename T, int P, int NW, int MODE, bool TMA, bool GLB, bool BWD>
-int launch_variant(const FusedParams<T>& p, const CUtensorMap& map, const Tiling& tl, int planes, cudaStream_t stream)
+int launch_variant(const FusedParams<T>& p, const CUtensorMap& map, const Tiling& tl, int planes, long grid_ctas, cudaStream_t stream)
 {
     auto kern = fused3x3_kernel<T, P, NW, MODE, TMA, GLB, BWD>;
     constexpr size_t smem = fused_smem_bytes<T, P, NW, MODE, TMA, BWD>();
@@ -1173,7 +1232,7 @@ int launch_variant(const FusedParams<T>& p, const CUtensorMap& map, const Tiling
     if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(tl.ntx * tl.cx), (unsigned)(tl.nty * tl.cy), (unsigned)planes);
+    cfg.gridDim = GLB ? dim3((unsigned)grid_ctas) : dim3((unsigned)(tl.ntx * tl.cx), (unsigned)(tl.nty * tl.cy), (unsigned)planes);
     cfg.blockDim = dim3(NW * 32);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
@@ -1257,26 +1316,24 @@ int launch(FusedParams<T> p, const Tiling& tl, int B, void* inbox, size_t inbox_
     p.cx = tl.cx; p.cy = tl.cy; p.ntx = tl.ntx; p.nty = tl.nty; p.stepx = tl.stepx; p.stepy = tl.stepy; p.ew = tl.ew; p.eh = tl.eh;
     p.margin = p.iters;
     const int planes = B * p.C;
-    // Exchange transport: DSMEM inside hardware clusters by default.  When the clusters would not all be resident
-    // at once (e.g. 8 NYU images = 8 clusters of 15 CTAs but the GPU places only 7) while the whole grid of CTAs
-    // would, drop the clusters and exchange through global memory instead: one wave instead of two.
-    bool glb = false;
-    const long ctas = tl.ctas * planes;
-    static const int force = [] { const char* v = getenv("CSPN_EXCHANGE"); return !v ? 0 : (!strcmp(v, "dsmem") ? 1 : (!strcmp(v, "global") ? 2 : 0)); }();   // debugging knob
-    if (force != 1 && tl.cx * tl.cy > 1 && inbox && inbox_avail >= (size_t)ctas * inbox_bytes<TH>() && ctas <= kMaxGlobalExchangeCtas && p.iters <= 60) {
-        const Capacity cap = capacity<P, NW, BWD>();
-        if (ctas <= cap.sms && (force == 2 || tl.cx * tl.cy > 16 || (long)tl.ntx * tl.nty * planes > cap.clusters[tl.cx * tl.cy])) glb = true;
-    }
-    if (!glb && tl.cx * tl.cy > 16) return CSPN_ERR_WORKSPACE;      // this tiling only exists for the global-memory exchange
+    // Exchange transport follows the tiling: hardware clusters talk through DSMEM, a streamed problem through inboxes
+    // in global memory (one per tile), walked by a persistent grid of at most one CTA per SM slot.
+    const bool glb = tl.stream;
+    long grid_ctas = 0;
     if (glb) {
+        const long total = tl.ctas * planes;
+        if (!inbox || inbox_avail < (size_t)total * inbox_bytes<TH>()) return CSPN_ERR_WORKSPACE;
+        const Capacity cap = capacity<P, NW, BWD>();
+        grid_ctas = total < cap.sms ? total : cap.sms;
+        p.total_tiles = (uint32_t)total;
         p.inbox = (uint4*)inbox;
         p.tag_base = exchange_epoch().fetch_add(1, std::memory_order_relaxed) << 7;      // + refresh index (1..120) is never 0
     }
     alignas(64) CUtensorMap map;
     memset(&map, 0, sizeof map);
     const bool tma = make_guidance_map<T, TH, MODE>(p.g, p.gbs, B, p.H, p.W, &map);      // false: unaligned guidance, plain-load prologue
-    if (glb) return tma ? launch_variant<T, P, NW, MODE, true, true, BWD>(p, map, tl, planes, stream) : launch_variant<T, P, NW, MODE, false, true, BWD>(p, map, tl, planes, stream);
-    return tma ? launch_variant<T, P, NW, MODE, true, false, BWD>(p, map, tl, planes, stream) : launch_variant<T, P, NW, MODE, false, false, BWD>(p, map, tl, planes, stream);
+    if (glb) return tma ? launch_variant<T, P, NW, MODE, true, true, BWD>(p, map, tl, planes, grid_ctas, stream) : launch_variant<T, P, NW, MODE, false, true, BWD>(p, map, tl, planes, grid_ctas, stream);
+    return tma ? launch_variant<T, P, NW, MODE, true, false, BWD>(p, map, tl, planes, 0, stream) : launch_variant<T, P, NW, MODE, false, false, BWD>(p, map, tl, planes, 0, stream);
 }
 
 }  // namespace

@@ -11,9 +11,8 @@ inline size_t up256(size_t v) { return (v + 255) & ~(size_t)255; }
 inline size_t hist_bytes(int iters) { return (size_t)kHistSlots * (size_t)iters * kTHBwd * kTileW * sizeof(float); }
 inline size_t bwd_inbox_bytes(const Tiling& tl, int B)
 {
-    if (tl.cx * tl.cy == 1) return 0;
-    const long ctas = tl.ctas * (long)B;
-    return ctas <= kMaxGlobalExchangeCtas ? up256((size_t)ctas * inbox_bytes<kTHBwd>()) : 0;
+    if (!tl.stream) return 0;
+    return up256((size_t)(tl.ctas * (long)B) * inbox_bytes<kTHBwd>());
 }
 }  // namespace
 
