@@ -1,6 +1,7 @@
 // C ABI of the CSPN B200 library (include/cspn_b200.h): argument validation, path selection
 // and the host-buffer convenience entry points.  No torch types anywhere in this library.
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 
 #include "cspn_common.cuh"
@@ -122,6 +123,40 @@ int backward_impl(const T* grad_out, const T* guidance, int64_t gbs, int Cg, con
     return rc;
 }
 
+// Per host thread and device state of the host entry points, created once:
+//  * a private stream-ordered memory pool that KEEPS its memory (release threshold = max): with the default pool every
+//    cudaStreamSynchronize hands the scratch back to the driver and the next call pays a fresh allocation (~0.3 ms);
+//  * two helper streams so the small depth / sparse copies overlap the guidance copy instead of queueing behind it
+//    (each small copy costs ~90 us on its own, tools/e2e_breakdown.py).
+constexpr int kAuxLanes = 2;
+struct HostCtx { bool ok; cudaMemPool_t pool; cudaStream_t s[kAuxLanes]; cudaEvent_t fork, join[kAuxLanes]; };
+HostCtx* host_ctx()
+{
+    static thread_local HostCtx ctxs[16] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) { cudaGetLastError(); return nullptr; }
+    HostCtx& c = ctxs[dev];
+    if (!c.ok) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        bool good = cudaMemPoolCreate(&c.pool, &props) == cudaSuccess;
+        if (good) {
+            unsigned long long keep = ~0ull;
+            good = cudaMemPoolSetAttribute(c.pool, cudaMemPoolAttrReleaseThreshold, &keep) == cudaSuccess;
+        }
+        good = good && cudaEventCreateWithFlags(&c.fork, cudaEventDisableTiming) == cudaSuccess;
+        for (int i = 0; good && i < kAuxLanes; ++i)
+            good = cudaStreamCreateWithFlags(&c.s[i], cudaStreamNonBlocking) == cudaSuccess &&
+                   cudaEventCreateWithFlags(&c.join[i], cudaEventDisableTiming) == cudaSuccess;
+        if (!good) { cudaGetLastError(); return nullptr; }
+        c.ok = true;
+    }
+    return &c;
+}
+
 // H2D -> forward -> D2H with stream-ordered scratch; returns once `out` holds the result.
 template <typename T>
 int forward_host_impl(const T* guidance, int64_t gbs, const T* depth, const T* sparse, int sparse_channels, T* out,
@@ -134,13 +169,16 @@ int forward_host_impl(const T* guidance, int64_t gbs, const T* depth, const T* s
     cudaStream_t stream = (cudaStream_t)stream_;
     const size_t hw = (size_t)H * W;
     // Only the K*K-1 channels that are read travel over PCIe; the device copy is packed (batch stride taps*H*W).
-    const size_t g_bytes = (size_t)B * tt.n * hw * sizeof(T), d_bytes = (size_t)B * C * hw * sizeof(T);
+    const size_t g_img = (size_t)tt.n * hw * sizeof(T);
+    const size_t g_bytes = (size_t)B * g_img, d_bytes = (size_t)B * C * hw * sizeof(T);
     const size_t s_bytes = sparse ? (size_t)B * sparse_channels * hw * sizeof(T) : 0;
     const size_t ws_bytes = cspn_fwd_workspace_bytes(B, C, H, W, iters, ksize, mode);
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
     const size_t total = up(g_bytes) + 2 * up(d_bytes) + up(s_bytes) + up(ws_bytes);
     char* base = nullptr;
-    cudaError_t e = cudaMallocAsync((void**)&base, total, stream);
+    static const bool plain = [] { const char* v = getenv("CSPN_HOST_PLAIN"); return v && atoi(v) == 1; }();     // A/B knob: default pool, one stream
+    HostCtx* ctx = plain ? nullptr : host_ctx();
+    cudaError_t e = ctx ? cudaMallocFromPoolAsync((void**)&base, total, ctx->pool, stream) : cudaMallocAsync((void**)&base, total, stream);
     if (e != cudaSuccess) return (int)e;
     char* p = base;
     T* dg = (T*)p; p += up(g_bytes);
@@ -148,10 +186,26 @@ int forward_host_impl(const T* guidance, int64_t gbs, const T* depth, const T* s
     T* dout = (T*)p; p += up(d_bytes);
     T* ds = sparse ? (T*)p : nullptr; p += up(s_bytes);
     void* dws = ws_bytes ? (void*)p : nullptr;
-    if (gbs == (int64_t)tt.n * (int64_t)hw) e = cudaMemcpyAsync(dg, guidance, g_bytes, cudaMemcpyHostToDevice, stream);
-    else e = cudaMemcpy2DAsync(dg, tt.n * hw * sizeof(T), guidance, (size_t)gbs * sizeof(T), tt.n * hw * sizeof(T), B, cudaMemcpyHostToDevice, stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(dd, depth, d_bytes, cudaMemcpyHostToDevice, stream);
-    if (e == cudaSuccess && sparse) e = cudaMemcpyAsync(ds, sparse, s_bytes, cudaMemcpyHostToDevice, stream);
+    const bool fork = ctx && g_bytes >= ((size_t)1 << 20);
+    cudaStream_t sd = fork ? ctx->s[0] : stream, ss = fork ? ctx->s[1] : stream;
+    if (fork) {
+        // the helper streams may touch the allocation only after it exists in `stream` order
+        e = cudaEventRecord(ctx->fork, stream);
+        for (int i = 0; e == cudaSuccess && i < kAuxLanes; ++i) e = cudaStreamWaitEvent(ctx->s[i], ctx->fork, 0);
+    }
+    if (e == cudaSuccess) {
+        if (gbs == (int64_t)tt.n * (int64_t)hw) e = cudaMemcpyAsync(dg, guidance, g_bytes, cudaMemcpyHostToDevice, stream);
+        else e = cudaMemcpy2DAsync(dg, g_img, guidance, (size_t)gbs * sizeof(T), g_img, (size_t)B, cudaMemcpyHostToDevice, stream);
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dd, depth, d_bytes, cudaMemcpyHostToDevice, sd);
+    if (e == cudaSuccess && sparse) e = cudaMemcpyAsync(ds, sparse, s_bytes, cudaMemcpyHostToDevice, ss);
+    if (fork)
+        for (int i = 0; i < kAuxLanes; ++i) {
+            // join even after an error: the free below is ordered on `stream`
+            cudaError_t ej = cudaEventRecord(ctx->join[i], ctx->s[i]);
+            if (ej == cudaSuccess) ej = cudaStreamWaitEvent(stream, ctx->join[i], 0);
+            if (e == cudaSuccess) e = ej;
+        }
     if (e == cudaSuccess) {
         rc = forward_impl<T>(dg, (int64_t)tt.n * (int64_t)hw, dd, ds, sparse_channels, dout, B, C, H, W, iters, ksize, mode, dws, ws_bytes, stream);
         if (rc == CSPN_OK) e = cudaMemcpyAsync(out, dout, d_bytes, cudaMemcpyDeviceToHost, stream);
