@@ -220,7 +220,7 @@ class _Null:
         return False
 
 
-def time_e2e(cfg, dev, steps):
+def time_e2e(cfg, dev, steps, dist=None):
     """The same metric through the host-buffer C-ABI call: pinned host inputs, H2D + kernel + D2H every step."""
     from cspn_monodepth_b200 import _lib
     lib = _lib.load()
@@ -256,16 +256,23 @@ def time_e2e(cfg, dev, steps):
     for i in range(3):
         call(i)
     torch.cuda.synchronize(dev)
+    if dist is not None:
+        dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(steps):
         call(i)
     e1.record()
     torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    if dist is not None:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
     esz = sets[0][0].element_size()
     h2d = (cg + 2) * b * h * w * esz
     d2h = b * h * w * esz
-    return e0.elapsed_time(e1) / steps, h2d, d2h, float(outs[0].float().mean())
+    return ms, h2d, d2h, float(outs[0].float().mean())
 
 
 def time_fwd_bwd(cfg, dev, steps):
@@ -396,6 +403,8 @@ def main():
     ms_step = ms_total / args.steps
     px_step = cfg["B"] * cfg["H"] * cfg["W"]
     value = world * px_step / (ms_step * 1e-3) / 1e6
+    # end-to-end leg on every rank at once (each GPU has its own PCIe link); the slowest rank sets the time
+    e_ms, h2d, d2h, _ = time_e2e(cfg, dev, min(args.steps, 50), dist)
     if rank == 0:
         peak, peak_src = hbm_peak()
         alg_bytes = BYTES_PER_PX[(cfg["dtype"], cfg["ksize"])] * px_step
@@ -408,9 +417,9 @@ def main():
                              "frac": achieved / peak, "traffic": ncu_traffic("nyu_b8_f32"), "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": alg_bytes, "launch_us": ms_step * 1e3,
                              "fma_floor_us": px_step * cfg["iters"] * 8 / (148 * 128 * 1.965e9) * 1e6}}
-        e_ms, h2d, d2h, _ = time_e2e(cfg, dev, min(args.steps, 50))
-        line["e2e"] = {"value": px_step / (e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                       "ms_per_step": e_ms, "api": "cspn_fwd_host_f32 (C ABI, host buffers in one pinned staging arena)", "n_gpus": 1}
+        line["e2e"] = {"value": world * px_step / (e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                       "ms_per_step": e_ms, "api": "cspn_fwd_host_f32 (C ABI, host buffers in one pinned staging arena), one call per rank and step",
+                       "n_gpus": world}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"], _ = cpu_reference(cfg)
             line["cpu_baseline_fused_c"] = cpu_c_oracle(cfg)

@@ -245,6 +245,19 @@ def test_fused_backward_iteration_counts(iters):
     _check_backward(1, 8, (1, 70, 200), iters, seed=iters + 100, density=None if iters == 3 else 0.05)
 
 
+@pytest.mark.parametrize("exchange", ["global", "dsmem"])
+def test_forced_exchange_modes(exchange):
+    """Both halo transports of the fused kernels on the same problems (the override is per process, hence the worker):
+    stream mode with several tiles per persistent CTA, hardware clusters with several cluster tiles per image."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CSPN_EXCHANGE=exchange)
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "exchange_modes_worker.py")], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok " + exchange), r.stdout[-2000:] + r.stderr[-4000:]
+
+
 # ---- size-independent properties at BASELINE.json's full sizes -------------------------------
 @pytest.mark.parametrize("path", PATHS)
 def test_full_size_properties(path):
