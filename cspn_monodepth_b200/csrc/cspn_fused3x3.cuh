@@ -220,12 +220,12 @@ template <int TH> struct InboxGeom {
 };
 __device__ __forceinline__ void st_ll(uint4* slot, u64 v, uint32_t tag)
 {
-    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %2};" :: "l"(slot), "r"(__float_as_uint(lo_of(v))), "r"(tag), "r"(__float_as_uint(hi_of(v))) : "memory");
+    asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %2};" :: "l"(slot), "r"(__float_as_uint(lo_of(v))), "r"(tag), "r"(__float_as_uint(hi_of(v))) : "memory");
 }
 __device__ __forceinline__ uint4 ld_ll(const uint4* slot)
 {
     uint4 v;
-    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(slot) : "memory");
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(slot) : "memory");
     return v;
 }
 
