@@ -1085,8 +1085,12 @@ fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant_
 }
 
 // ---- host side: pick the cluster shape and the tiling ----------------------------------------------------
-constexpr int kNW = 8;                        // warps per CTA of the one-CTA-per-SM variants
-constexpr int kPFwd = 10;                     // forward: 64 x 80 pixel register tile per CTA
+#ifndef CSPN_FWD_WARPS
+#define CSPN_FWD_WARPS 8
+#define CSPN_FWD_ROWS 10
+#endif
+constexpr int kNW = CSPN_FWD_WARPS;           // forward: warps per CTA (one CTA per SM) ...
+constexpr int kPFwd = CSPN_FWD_ROWS;          // ... x rows per warp: 64 x 80 pixel register tile per CTA
 #ifndef CSPN_BWD_WARPS
 #define CSPN_BWD_WARPS 8
 #endif
