@@ -22,3 +22,15 @@ def golden():
         name, field = key.split("/")
         cases.setdefault(name, {})[field] = z[key]
     return cases
+
+
+@pytest.fixture(scope="session")
+def unet_golden():
+    """What the reference's own UNets hand to the CSPN module, and the reference module's results on it
+    (tests/golden/make_unet_golden.py): realistic value distribution (small, smooth guidance; 12 channels in mode A)."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "cspn_unet_heads.npz"))
+    cases = {}
+    for key in z.files:
+        name, field = key.split("/")
+        cases.setdefault(name, {})[field] = z[key]
+    return cases

@@ -216,6 +216,22 @@ def test_backward_vs_oracle_larger(path):
         assert_close_nan(tg.grad.cpu().numpy(), gg, GRAD_RTOL * max(1.0, np.abs(gg).max()), f"gg mode {mode} k {k}")
 
 
+@pytest.mark.parametrize("path", PATHS)
+def test_unet_head_vectors(unet_golden, path):
+    """The tensors the reference's own UNets hand to the module (12-channel guidance of magnitude 1e-2, smooth depth):
+    forward and gradients against the reference module's results, tolerance relative to the value range."""
+    _lib.load().cspn_set_path(path)
+    for name, case in sorted(unet_golden.items()):
+        mode, _, iters = case_config(name, case)
+        y, tg, td = _run(mode, case["guidance"], case["depth"], case["sparse"], iters, requires_grad=True)
+        y.backward(_cu(case["grad_out"]))
+        assert_close_nan(y.detach().cpu().numpy(), case["out"], 1e-5 * np.abs(case["out"]).max(), name + ":out")
+        for got, key in ((td.grad, "grad_depth"), (tg.grad, "grad_guidance")):
+            assert_close_nan(got.cpu().numpy(), case[key], GRAD_RTOL * np.abs(case[key]).max(), f"{name}:{key}")
+        if mode == 0:
+            assert torch.count_nonzero(tg.grad[:, 8:]) == 0
+
+
 def _check_backward(mode, cg, shape, iters, seed, density=0.03, expect_fused=True):
     b, h, w = shape
     g, d, s = make_inputs(seed, b, cg, 1, h, w, density=density)

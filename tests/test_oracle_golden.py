@@ -132,3 +132,24 @@ def test_torch_port_matches_reference(golden):
         s = torch.from_numpy(case["sparse"]) if "sparse" in case else None
         y = torch_port.mode_a_forward(g, d, s, iters) if mode == 0 else torch_port.mode_b_forward(d, g, s, iters)
         assert_close_nan(y.numpy(), case["out"], 1e-5 * max(1.0, float(np.nanmax(np.abs(case["depth"]))) / 10.0), name)
+
+
+@pytest.mark.parametrize("impl", ["numpy", "c"])
+def test_unet_head_vectors(unet_golden, impl):
+    """Inputs with the distribution the reference UNets really produce (|guidance| ~ 1e-2, depth ~ 1e-2 at random
+    initialisation): the tolerance is relative to the value range (north_star: 1e-4 at range 10 = 1e-5 relative)."""
+    for name, case in sorted(unet_golden.items()):
+        mode, ksize, iters = case_config(name, case)
+        g, d, s, go = case["guidance"], case["depth"], case["sparse"], case["grad_out"]
+        if impl == "numpy":
+            y = cspn_oracle.mode_a_forward(g, d, s, iters) if mode == 0 else cspn_oracle.mode_b_forward(d, g, s, iters)
+            if mode == 0:
+                gg, gd = cspn_oracle.mode_a_backward(g, d, s, go, iters)
+            else:
+                gd, gg = cspn_oracle.mode_b_backward(d, g, s, go, iters)
+        else:
+            y = c_oracle.forward(g, d, s, iters, ksize, mode)
+            gg, gd = c_oracle.backward(g, d, s, go, iters, ksize, mode)
+        assert_close_nan(y, case["out"], 1e-5 * np.abs(case["out"]).max(), f"{impl}:{name}:out")
+        assert_close_nan(gd, case["grad_depth"], GRAD_RTOL * np.abs(case["grad_depth"]).max(), f"{impl}:{name}:grad_depth")
+        assert_close_nan(gg, case["grad_guidance"], GRAD_RTOL * np.abs(case["grad_guidance"]).max(), f"{impl}:{name}:grad_guidance")
