@@ -50,6 +50,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = []
     procs = []
     extra = ["-DCSPN_TRACE"] if os.environ.get("CSPN_TRACE") else []
+    if os.environ.get("CSPN_PACKED_SWEEP"):        # A/B: FFMA2 (packed f32x2) sweeps instead of the scalar-FMA default
+        extra += ["-DCSPN_PACKED_SWEEP"]
     if os.environ.get("CSPN_FWD_TILE"):            # experiments: "warps x rows", e.g. 12x7
         wv, rw = os.environ["CSPN_FWD_TILE"].split("x")
         extra += [f"-DCSPN_FWD_WARPS={int(wv)}", f"-DCSPN_FWD_ROWS={int(rw)}"]
