@@ -75,3 +75,22 @@ def test_workspace_queries():
         lib.cspn_set_path(prev)
     assert lib.cspn_bwd_workspace_bytes(1, 1, 16, 16, 24, 3, 0) >= (8 + 8 + 1 + 23 + 3) * 256 * 4
     assert lib.cspn_bwd_workspace_bytes(1, 1, 16, 16, 24, 4, 0) == 0
+
+
+def test_planner_picks_transport_by_problem_size():
+    """The workspace query runs the same planner as the launch (B200 cluster capacities as defaults without a GPU):
+    hardware clusters need no scratch, stream mode one 16-byte-slot inbox per tile (576 slots for a 64x80 tile), the
+    blocked 5x5 path two fp32 planes, the fused backward the per-SM history (192 slots x T x 64 x 64 floats)."""
+    lib = _lib.load()
+    inbox = (4 * 80 + 4 * 2 * 32) * 16
+    assert lib.cspn_fwd_workspace_bytes(1, 1, 228, 304, 24, 3, 0) == 0                 # one 5x3 cluster: DSMEM
+    assert lib.cspn_fwd_workspace_bytes(7, 1, 228, 304, 24, 3, 0) == 0                 # 7 clusters of 15 fit at once
+    assert lib.cspn_fwd_workspace_bytes(8, 1, 228, 304, 24, 3, 0) == 8 * 15 * inbox    # the 8th would not: stream mode, 120 tiles
+    assert lib.cspn_fwd_workspace_bytes(32, 1, 352, 1216, 24, 3, 0) == 0               # KITTI batch: 4x2 hardware clusters
+    assert lib.cspn_fwd_workspace_bytes(8, 1, 64, 64, 24, 3, 0) == 0                   # single-tile images
+    assert lib.cspn_fwd_workspace_bytes(16, 1, 480, 640, 12, 5, 1) == 2 * 16 * 480 * 640 * 4
+    assert lib.cspn_fwd_workspace_bytes(16, 1, 480, 640, 4, 5, 1) == 0                 # one launch: no hand-over planes
+    hist = 192 * 24 * 64 * 64 * 4
+    assert lib.cspn_bwd_workspace_bytes(1, 1, 60, 60, 24, 3, 0) == hist                # one tile: history only
+    n = lib.cspn_bwd_workspace_bytes(8, 1, 228, 304, 24, 3, 0)
+    assert n == hist + 8 * 20 * (4 * 64 + 4 * 2 * 32) * 16                             # stream mode: 20 tiles of 64x64 per image
