@@ -128,6 +128,10 @@ blocked5x5_kernel(const T* __restrict__ g, int64_t gbs, const TIn* __restrict__ 
         const float(*cur)[kSW] = buf[s & 1];
 #pragma unroll
         for (int q = 0; q < kQuad; ++q) acc[q] = cq[q];
+        // rows that can no longer reach the exact inner block are not computed (a warp owns two whole rows, so the
+        // test is warp-uniform): the last step only needs the inner rows, the one before 2 more on each side, ...
+        const int live = halo_y - 2 * (steps - 1 - s);
+        if (ry >= live && ry < kRH - live) {
 #pragma unroll
         for (int dy = -2; dy <= 2; ++dy) {
             const float* row = &cur[ry + kPadY + dy][kPadX + qx * kQuad];
@@ -143,6 +147,7 @@ blocked5x5_kernel(const T* __restrict__ g, int64_t gbs, const TIn* __restrict__ 
 #pragma unroll
                 for (int q = 0; q < kQuad; ++q) acc[q] = fmaf(w[q][j], v[4 + q + dx], acc[q]);
             }
+        }
         }
         *reinterpret_cast<float4*>(&buf[(s + 1) & 1][ry + kPadY][kPadX + qx * kQuad]) = make_float4(acc[0], acc[1], acc[2], acc[3]);
         __syncthreads();
