@@ -490,6 +490,14 @@ __device__ __forceinline__ void fused_tile(const FusedParams<T>& p, const CUtens
     constexpr uint32_t kColPar = sizeof(float) * 2 * TH * 2, kColSide = sizeof(float) * TH * 2;
     constexpr uint32_t kRowPar = sizeof(float) * 2 * kHaloY * kTileW, kRowSide = sizeof(float) * kHaloY * kTileW;
 
+    // The re-injection term c = m*d0 moves out of the register file: it is read once per row and step, while the 20
+    // registers it occupied let the compiler keep the loop invariants of the halo exchange instead of rebuilding them
+    // every step.  It lives where the guidance was staged (dead from here on; each thread only re-reads its own words).
+    u64* const ctile = reinterpret_cast<u64*>(smem_raw + sizeof(Smem<NW, P>)) + (warp * P) * 32 + lane;
+    __syncthreads();                                     // every warp has taken its guidance out of the staging buffer
+#pragma unroll
+    for (int i = 0; i < P; ++i) ctile[i * 32] = cc[i];
+
     TRACE(12);
     if (hw_cluster) cluster_wait();
     TRACE(13);
@@ -604,7 +612,8 @@ __device__ __forceinline__ void fused_tile(const FusedParams<T>& p, const CUtens
             const float l = __shfl_up_sync(0xffffffffu, hi, 1), rr = __shfl_down_sync(0xffffffffu, lo, 1);
             if (r + 1 < P) {
                 const int i = r + 1;
-                float x0 = lo_of(cc[i]), x1 = hi_of(cc[i]);
+                const u64 ci = ctile[i * 32];
+                float x0 = lo_of(ci), x1 = hi_of(ci);
                 x0 = fmaf(lo_of(nw[i][0]), l, x0);   x1 = fmaf(hi_of(nw[i][0]), lo, x1);
                 x0 = fmaf(lo_of(nw[i][1]), lo, x0);  x1 = fmaf(hi_of(nw[i][1]), hi, x1);
                 a0[i] = fmaf(lo_of(nw[i][2]), hi, x0); a1[i] = fmaf(hi_of(nw[i][2]), rr, x1);
@@ -640,7 +649,7 @@ __device__ __forceinline__ void fused_tile(const FusedParams<T>& p, const CUtens
             u64 s1, s2;
             shifted(src, s1, s2);
             if (r + 1 < P) {
-                u64 a = cc[r + 1];
+                u64 a = ctile[(r + 1) * 32];
                 a = fma2(nw[r + 1][0], s1, a);
                 a = fma2(nw[r + 1][1], src, a);
                 acc[r + 1] = fma2(nw[r + 1][2], s2, a);
@@ -1273,7 +1282,9 @@ constexpr size_t fused_smem_bytes()
 {
     constexpr size_t stage = TMA ? Stage<T, NW * P, MODE>::bytes : 0;
     constexpr size_t tiles = BWD ? BwdTiles<NW * P>::bytes : 0;
-    return sizeof(Smem<NW, P>) + (stage > tiles ? stage : tiles) + (BWD ? BwdTiles<NW * P>::stash_bytes : 0);
+    constexpr size_t ctile = (size_t)NW * P * 32 * sizeof(u64);      // re-injection tile (aliases the staging buffer)
+    constexpr size_t dyn = stage > tiles ? (stage > ctile ? stage : ctile) : (tiles > ctile ? tiles : ctile);
+    return sizeof(Smem<NW, P>) + dyn + (BWD ? BwdTiles<NW * P>::stash_bytes : 0);
 }
 
 template <typename T, int P, int NW, int MODE, bool TMA, bool GLB, bool BWD>
