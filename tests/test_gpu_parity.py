@@ -297,6 +297,34 @@ def test_full_size_properties(path):
         assert (y2.float() - yf).abs().max().item() < (1e-4 if dtype == torch.float32 else 2e-2)
 
 
+def test_full_size_backward_properties():
+    """Oracle-free properties of the fused backward at BASELINE.json's full sizes: gradient mass
+    (sum of d(sum out)/d depth = number of pixels, mode A with a 0/1 mask), exact linearity in grad_out for a factor 2,
+    zero gradient for the guidance channels that are not read, and batch-slice independence bit for bit although the
+    full batch and the slice run with different tilings / halo transports."""
+    for (b, h, w, dtype) in ((8, 228, 304, torch.float32), (4, 352, 1216, torch.float32)):
+        g, d, s = make_inputs(7 * b + h, b, 12, 1, h, w, density=0.01)
+        y, tg, td = _run(0, g, d, s, 24, requires_grad=True, dtype=dtype)
+        assert _lib.load().cspn_last_path() == _lib.PATH_FUSED
+        y.backward(torch.ones_like(y))
+        assert _lib.load().cspn_last_path() == _lib.PATH_FUSED and _lib.load().cspn_last_launch_count() == 1
+        gd1, gg1 = td.grad.clone(), tg.grad.clone()
+        assert torch.isfinite(gd1).all() and torch.isfinite(gg1).all()
+        mass = gd1.double().sum().item()
+        assert abs(mass - b * h * w) <= 1e-4 * b * h * w, f"gradient mass {mass} vs {b * h * w}"
+        assert torch.count_nonzero(gg1[:, 8:]) == 0
+        go = torch.from_numpy(np.random.default_rng(b).standard_normal(d.shape).astype(np.float32)).to(DEV)
+        grads = []
+        for scale in (1.0, 2.0):
+            y, tg, td = _run(0, g, d, s, 24, requires_grad=True, dtype=dtype)
+            y.backward(go * scale)
+            grads.append((td.grad.clone(), tg.grad.clone()))
+        assert torch.equal(grads[1][0], grads[0][0] * 2) and torch.equal(grads[1][1], grads[0][1] * 2)
+        y, tg, td = _run(0, g[1:3], d[1:3], s[1:3], 24, requires_grad=True, dtype=dtype)
+        y.backward(go[1:3])
+        assert torch.equal(td.grad, grads[0][0][1:3]) and torch.equal(tg.grad, grads[0][1][1:3])
+
+
 def test_extra_and_strided_guidance_channels():
     g, d, s = make_inputs(31, 2, 12, 1, 33, 47, density=0.05)
     y12, _, _ = _run(0, g, d, s, 24)
