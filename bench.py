@@ -119,6 +119,33 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process (and thereby its first-touch host allocations, e.g. the pinned staging arena) to the CPUs that
+    sit on the same NUMA node as GPU `index`: with 8 ranks the H2D copies otherwise cross the socket interconnect.
+    Best effort - returns a short description or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dev_dir = "/sys/bus/pci/devices/" + bus.lower()[-12:]
+        with open(dev_dir + "/local_cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        with open(dev_dir + "/numa_node") as f:
+            node = f.read().strip()
+        return f"numa node {node}, {len(cpus)} cpus"
+    except Exception:
+        return None
+
+
 def hbm_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -393,6 +420,7 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None     # host buffers next to their GPU
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -419,7 +447,7 @@ def main():
                              "fma_floor_us": px_step * cfg["iters"] * 8 / (148 * 128 * 1.965e9) * 1e6}}
         line["e2e"] = {"value": world * px_step / (e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                        "ms_per_step": e_ms, "api": "cspn_fwd_host_f32 (C ABI, host buffers in one pinned staging arena), one call per rank and step",
-                       "n_gpus": world}
+                       "n_gpus": world, "host_binding": numa}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"], _ = cpu_reference(cfg)
             line["cpu_baseline_fused_c"] = cpu_c_oracle(cfg)
