@@ -19,6 +19,9 @@ CFGS = {
     "nyu16": dict(B=8, H=228, W=304, iters=24, ksize=3, mode=0, dtype=torch.float16),
     "kitti": dict(B=32, H=352, W=1216, iters=24, ksize=3, mode=0, dtype=torch.float16),
     "kitti32": dict(B=32, H=352, W=1216, iters=24, ksize=3, mode=0, dtype=torch.float32),
+    "kitti1": dict(B=1, H=352, W=1216, iters=24, ksize=3, mode=0, dtype=torch.float16),
+    "nyu7": dict(B=7, H=228, W=304, iters=24, ksize=3, mode=0, dtype=torch.float32),
+    "nyu9": dict(B=9, H=228, W=304, iters=24, ksize=3, mode=0, dtype=torch.float32),
     "kitti4": dict(B=4, H=352, W=1216, iters=24, ksize=3, mode=0, dtype=torch.float16),
     "pac3": dict(B=8, H=228, W=304, iters=24, ksize=3, mode=1, dtype=torch.float32),
     "pac5": dict(B=16, H=480, W=640, iters=12, ksize=5, mode=1, dtype=torch.float32),
