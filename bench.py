@@ -285,13 +285,16 @@ def time_e2e(cfg, dev, steps, dist=None):
     torch.cuda.synchronize(dev)
     if dist is not None:
         dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(steps):
-        call(i)
-    e1.record()
-    torch.cuda.synchronize(dev)
-    ms = e0.elapsed_time(e1) / steps
+    blocks = []
+    for _ in range(3):                      # median of three blocks of `steps` calls: host-side copies are noisy on shared boxes
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            call(i)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        blocks.append(e0.elapsed_time(e1) / steps)
+    ms = statistics.median(blocks)
     if dist is not None:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
