@@ -22,6 +22,7 @@ SIGNATURES = {
     "cspn_last_launch_count": (_c_int, []),
     "cspn_fwd_workspace_bytes": (_c_sz, [_c_int] * 7),
     "cspn_bwd_workspace_bytes": (_c_sz, [_c_int] * 7),
+    "cspn_fwd_plan": (_c_int, [_c_int] * 7 + [ctypes.POINTER(_c_int)]),
     "cspn_fwd_f32": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_int, _c_vp] + [_c_int] * 7 + [_c_vp, _c_sz, _c_vp]),
     "cspn_fwd_f16": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_int, _c_vp] + [_c_int] * 7 + [_c_vp, _c_sz, _c_vp]),
     "cspn_bwd_f32": (_c_int, [_c_vp, _c_vp, _c_i64, _c_int, _c_vp, _c_vp, _c_int, _c_vp, _c_vp] + [_c_int] * 7 + [_c_vp, _c_sz, _c_vp]),
@@ -72,6 +73,17 @@ def load() -> ctypes.CDLL:
             fn.restype, fn.argtypes = res, args
         _lib = lib
     return _lib
+
+
+KERNEL_GENERIC, KERNEL_SINGLE, KERNEL_DUAL, KERNEL_BLOCKED = 0, 1, 2, 3
+
+
+def forward_plan(b: int, c: int, h: int, w: int, iters: int, ksize: int = 3, mode: int = MODE_NEW) -> dict:
+    """What the planner picks for a forward problem on the current device (``cspn_fwd_plan``)."""
+    buf = (_c_int * 10)()
+    check(load().cspn_fwd_plan(b, c, h, w, iters, ksize, mode, buf))
+    keys = ("kernel", "rows_per_warp", "cx", "cy", "ntx", "nty", "ctas", "rounds", "units_per_class", "units")
+    return dict(zip(keys, list(buf)))
 
 
 def check(code: int) -> None:

@@ -38,10 +38,10 @@ bool overlaps(const void* a, size_t an, const void* b, size_t bn)
     return a && b && pa < pb + bn && pb < pa + an;
 }
 
-bool use_fused(int C, int H, int W, int iters, int ksize, int mode, int* err)
+bool use_fused(int B, int C, int H, int W, int iters, int ksize, int mode, int* err)
 {
     const int path = g_path.load(std::memory_order_relaxed);
-    const bool ok = fused_supported(C, H, W, iters, ksize, mode);
+    const bool ok = fused_supported(B, C, H, W, iters, ksize, mode);
     if (path == CSPN_PATH_FUSED && !ok && err) *err = CSPN_ERR_BAD_KERNEL_SIZE;
     return path != CSPN_PATH_GENERIC && ok;
 }
@@ -74,10 +74,12 @@ int forward_impl(const T* guidance, int64_t gbs, const T* depth, const T* sparse
     FwdArgs<T> a{guidance, gbs, depth, sparse, sparse ? sparse_channels : 1, out, B, C, H, W, iters, ksize, mode, ws, ws_bytes, (cudaStream_t)stream};
     call_stats().launches = 0;
     int err = CSPN_OK;
-    if (iters > 0 && use_fused(C, H, W, iters, ksize, mode, &err)) {
+    if (iters > 0 && use_fused(B, C, H, W, iters, ksize, mode, &err)) {
         rc = fused_forward<T>(a);
         if (rc == CSPN_OK) call_stats().path = CSPN_PATH_FUSED;
-        return rc;
+        if (rc != kDualFallback) return rc;
+        // no fused kernel took the problem after all (guidance not TMA-addressable and no single-tile plan)
+        if (g_path.load(std::memory_order_relaxed) == CSPN_PATH_FUSED) return CSPN_ERR_BAD_KERNEL_SIZE;
     }
     if (err != CSPN_OK) return err;
     if (iters > 0 && use_blocked(B, C, H, W, iters, ksize, mode)) {
@@ -257,9 +259,29 @@ size_t cspn_fwd_workspace_bytes(int B, int C, int H, int W, int iters, int ksize
 {
     TapTable tt;
     if (!make_taps(mode, ksize, &tt) || B < 1 || C < 1 || H < 1 || W < 1 || iters < 1) return 0;
-    if (use_fused(C, H, W, iters, ksize, mode, nullptr)) return fused_workspace(B, C, H, W, iters);
+    if (use_fused(B, C, H, W, iters, ksize, mode, nullptr)) {
+        // a dual-slot-only problem may still fall through to the generic path at launch time (unaligned guidance pointer)
+        const size_t f = fused_workspace(B, C, H, W, iters, ksize, mode);
+        const size_t g = generic_fwd_workspace(B, C, H, W, tt.n);
+        return fused_single_possible(B, C, H, W, iters) ? f : (f > g ? f : g);
+    }
     if (use_blocked(B, C, H, W, iters, ksize, mode)) return blocked5x5_workspace(B, C, H, W, iters);
     return generic_fwd_workspace(B, C, H, W, tt.n);
+}
+
+int cspn_fwd_plan(int B, int C, int H, int W, int iters, int ksize, int mode, int* plan10)
+{
+    TapTable tt;
+    if (!plan10) return CSPN_ERR_NULL_POINTER;
+    for (int i = 0; i < 10; ++i) plan10[i] = 0;
+    if (!make_taps(mode, ksize, &tt)) return CSPN_ERR_BAD_KERNEL_SIZE;
+    if (B < 1 || C < 1 || H < 1 || W < 1 || iters < 1) return CSPN_ERR_BAD_SHAPE;
+    if (use_fused(B, C, H, W, iters, ksize, mode, nullptr)) {
+        if (dual_supported(B, C, H, W, iters, ksize, mode)) { plan10[0] = CSPN_KERNEL_DUAL; dual_describe(B, C, H, W, iters, plan10 + 1); }
+        else plan10[0] = CSPN_KERNEL_SINGLE;
+    } else if (use_blocked(B, C, H, W, iters, ksize, mode)) plan10[0] = CSPN_KERNEL_BLOCKED;
+    else plan10[0] = CSPN_KERNEL_GENERIC;
+    return CSPN_OK;
 }
 
 size_t cspn_bwd_workspace_bytes(int B, int C, int H, int W, int iters, int ksize, int mode)

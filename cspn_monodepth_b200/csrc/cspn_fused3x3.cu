@@ -21,27 +21,48 @@ Tiling plan_forward(int B, int C, int H, int W, int iters)
 }
 }  // namespace
 
-bool fused_supported(int C, int H, int W, int iters, int ksize, int mode)
+// The single-tile kernel can run the problem: the planner (same inputs as the launch: real device capacity, all
+// planes) finds a tiling and the plane count fits gridDim.z.
+static bool single_ok(int B, int C, int H, int W, int iters)
 {
-    (void)C; (void)mode;
-    if (ksize != 3 || iters < 1) return false;
-    if ((long)H * W > (1l << 30)) return false;
-    return choose_tiling(H, W, iters, kTHBig, 1, default_capacity()).ok;
+    if ((long)H * W > (1l << 30) || (long)B * C > 65535) return false;
+    return plan_forward(B, C, H, W, iters).ok;
 }
 
-size_t fused_workspace(int B, int C, int H, int W, int iters)
+bool fused_single_possible(int B, int C, int H, int W, int iters) { return single_ok(B, C, H, W, iters); }
+
+bool fused_supported(int B, int C, int H, int W, int iters, int ksize, int mode)
 {
+    if (ksize != 3 || iters < 1 || B < 1) return false;
+    return dual_supported(B, C, H, W, iters, ksize, mode) || single_ok(B, C, H, W, iters);
+}
+
+static size_t single_workspace(int B, int C, int H, int W, int iters)
+{
+    if (!single_ok(B, C, H, W, iters)) return 0;
     const Tiling tl = plan_forward(B, C, H, W, iters);
-    if (!tl.ok || !tl.stream) return 0;
+    if (!tl.stream) return 0;
     return (size_t)(tl.ctas * (long)B * C) * inbox_bytes<kTHBig>();     // inboxes of the global-memory exchange, one per tile
+}
+
+// Sized for whichever kernel the launch ends up with: the dual-slot kernel can still hand over to the single-tile one
+// at launch time (guidance pointer / batch stride not TMA-addressable).
+size_t fused_workspace(int B, int C, int H, int W, int iters, int ksize, int mode)
+{
+    const size_t a = dual_supported(B, C, H, W, iters, ksize, mode) ? dual_workspace(B, C, H, W, iters) : 0;
+    const size_t b = single_workspace(B, C, H, W, iters);
+    return a > b ? a : b;
 }
 
 template <typename T>
 int fused_forward(const FwdArgs<T>& a)
 {
+    if (dual_supported(a.B, a.C, a.H, a.W, a.iters, a.ksize, a.mode)) {
+        const int rc = dual_forward<T>(a);
+        if (rc != kDualFallback) return rc;
+    }
+    if (!single_ok(a.B, a.C, a.H, a.W, a.iters)) return kDualFallback;       // nothing fused fits: the caller falls through
     const Tiling tl = plan_forward(a.B, a.C, a.H, a.W, a.iters);
-    if (!tl.ok) return CSPN_ERR_BAD_KERNEL_SIZE;
-    if ((long)a.B * a.C > 65535) return CSPN_ERR_BAD_SHAPE;
     FusedParams<T> p = forward_params(a);
     return a.mode == CSPN_MODE_NEW ? launch<T, kPFwd, kNW, CSPN_MODE_NEW, false>(p, tl, a.B, a.ws, a.ws_bytes, a.stream)
                                    : launch<T, kPFwd, kNW, CSPN_MODE_OURS, false>(p, tl, a.B, a.ws, a.ws_bytes, a.stream);

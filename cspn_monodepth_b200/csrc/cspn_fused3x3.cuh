@@ -1227,14 +1227,16 @@ inline Tiling choose_tiling(int H, int W, int iters, int th, long planes, const 
         t.ctas = (long)t.cx * t.cy; t.ok = true;
         const long total = t.ctas * planes;
         const long grid = total < cap.sms ? total : cap.sms;
-        if (t.cx * t.cy > 1 && t.cx + 1 < grid && total <= kMaxGlobalExchangeCtas) {
-            // All tiles of an image advance in lockstep, so the grid effectively works on floor(slots / tiles per image)
-            // images at a time (measured: 32 KITTI images of 105 tiles take 32 tile times on 148 SMs); an image larger
-            // than the GPU is walked as a wavefront with stalls at the round boundaries.
-            const long per_image = t.ctas;
-            double cost;
-            if (per_image <= cap.sms) { const long groups = cap.sms / per_image; cost = (double)((planes + groups - 1) / groups); }
-            else cost = 1.5 * (double)total / (double)cap.sms;
+        // All tiles of an image advance in lockstep (every refresh waits for all four neighbours), so a tile e refreshes
+        // into the loop needs the tile e hops away to have STARTED: an image with more tiles than the persistent grid has
+        // CTAs would wait on tiles that only start when earlier ones finish - a circular wait.  Stream mode is therefore
+        // only offered when a whole image is resident at once; larger images run as hardware clusters with margins (or,
+        // forward, through the dual-slot kernel, which cuts them into resident units).
+        if (t.cx * t.cy > 1 && t.ctas <= cap.sms && total <= kMaxGlobalExchangeCtas) {
+            // the grid effectively works on floor(slots / tiles per image) images at a time (measured: 32 KITTI images of
+            // 105 tiles take 32 tile times on 148 SMs)
+            const long groups = cap.sms / t.ctas;
+            double cost = (double)((planes + groups - 1) / groups);
             if (exchange_override() == 2) cost = 0.0;
             consider(t, cost);
         }

@@ -93,6 +93,16 @@ CSPN_API int cspn_last_launch_count(void);
 CSPN_API size_t cspn_fwd_workspace_bytes(int B, int C, int H, int W, int iters, int ksize, int mode);
 CSPN_API size_t cspn_bwd_workspace_bytes(int B, int C, int H, int W, int iters, int ksize, int mode);
 
+/* Diagnostics: which forward kernel the planner picks for a problem on the current device (what the launch will use
+ * for TMA-addressable guidance).  plan10[0] = CSPN_KERNEL_*; for CSPN_KERNEL_DUAL the rest is {rows per warp P (tile =
+ * 64 x 8P pixels), tiles per unit cx, cy, units per image plane ntx, nty, CTAs, rounds, units per class and round,
+ * units}; zeros otherwise.  Not needed to call the operators. */
+#define CSPN_KERNEL_GENERIC 0
+#define CSPN_KERNEL_SINGLE 1  /* one 64 x 80 register tile per CTA, hardware clusters (DSMEM) or persistent stream (cspn_fused3x3.cuh) */
+#define CSPN_KERNEL_DUAL 2    /* two register tiles per CTA worked on alternately, halo messages through L2 (cspn_dual3x3.cu) */
+#define CSPN_KERNEL_BLOCKED 3 /* temporally blocked 5x5 (cspn_blocked5x5.cu) */
+CSPN_API int cspn_fwd_plan(int B, int C, int H, int W, int iters, int ksize, int mode, int* plan10);
+
 /* Forward: out[B,C,H,W] = r^iters. iters == 0 copies depth to out. */
 CSPN_API int cspn_fwd_f32(const float* guidance, int64_t guidance_batch_stride,
                  const float* depth, const float* sparse, int sparse_channels, float* out,

@@ -22,6 +22,29 @@ def cu(a):
     return None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 
 
+def check16(mode, shape, iters, seed):
+    """fp16 storage (BASELINE configs[2]'s precision) against the oracle on the fp16-rounded inputs: 1 fp16 ulp of the
+    element + the fp32 tolerance."""
+    b, h, w = shape
+    g, d, s = (a.astype(np.float16) for a in make_inputs(seed, b, 8, 1, h, w, density=0.03))
+    go = np.random.default_rng(seed + 7).standard_normal(d.shape).astype(np.float16)
+    tg, td, ts = (cu(a) for a in (g, d, s))
+    tg.requires_grad_(True); td.requires_grad_(True)
+    mod = cspn_new.AffinityPropagate(iters, 3) if mode == 0 else cspn_ours.AffinityPropagate(iters)
+    y = mod(tg, td, ts) if mode == 0 else mod(td, tg, sparse_depth=ts)
+    assert lib.cspn_last_path() == _lib.PATH_FUSED
+    f32 = [a.astype(np.float32) for a in (g, d, s, go)]
+    ref = c_oracle.forward(f32[0], f32[1], f32[2], iters, 3, mode, threads=0)
+    err = np.abs(y.detach().float().cpu().numpy() - ref)
+    assert (err <= np.abs(ref) * 2.0 ** -10 + 1e-4).all(), f"fp16 forward {shape} mode {mode}: {err.max():.3e}"
+    y.backward(cu(go))
+    assert lib.cspn_last_path() == _lib.PATH_FUSED and lib.cspn_last_launch_count() == 1
+    gg, gd = c_oracle.backward(f32[0], f32[1], f32[2], f32[3], iters, 3, mode, threads=0)
+    for got, want, what in ((td.grad, gd, "grad_depth"), (tg.grad, gg, "grad_guidance")):
+        e = np.abs(got.float().cpu().numpy() - want)
+        assert (e <= np.abs(want) * 2.0 ** -10 + 1e-4 * max(1.0, np.abs(want).max())).all(), f"fp16 {what} {shape} mode {mode}: {e.max():.3e}"
+
+
 def check(mode, shape, iters, seed, backward):
     b, h, w = shape
     g, d, s = make_inputs(seed, b, 8, 1, h, w, density=0.03)
@@ -48,6 +71,10 @@ def check(mode, shape, iters, seed, backward):
 # 12 x 15 = 180 forward tiles / 12 x 20 = 240 backward tiles on 148 SMs; 30 KITTI-ish tiles per image; ragged small ones
 for mode, shape, iters in ((0, (12, 228, 304), 24), (1, (3, 352, 500), 24), (0, (40, 97, 131), 7), (0, (2, 352, 1216), 24), (1, (5, 65, 257), 3)):
     check(mode, shape, iters, seed=shape[1] + iters, backward=True)
+
+# BASELINE configs[1] / [2] shapes in fp16 through the forced transport (forward and backward)
+for mode, shape in ((0, (8, 228, 304)), (0, (2, 352, 1216)), (1, (3, 228, 304))):
+    check16(mode, shape, 24, seed=shape[0] + shape[2])
 
 # CUDA graph: capture one forward, replay it twice, compare with the eager result
 g, d, s = make_inputs(5, 10, 8, 1, 228, 304, density=0.02)

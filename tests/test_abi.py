@@ -77,17 +77,32 @@ def test_workspace_queries():
     assert lib.cspn_bwd_workspace_bytes(1, 1, 16, 16, 24, 4, 0) == 0
 
 
-def test_planner_picks_transport_by_problem_size():
-    """The workspace query runs the same planner as the launch (B200 cluster capacities as defaults without a GPU):
-    hardware clusters need no scratch, stream mode one 16-byte-slot inbox per tile (576 slots for a 64x80 tile), the
-    blocked 5x5 path two fp32 planes, the fused backward the per-SM history (192 slots x T x 64 x 64 floats)."""
+def test_planner_picks_kernel_and_workspace_by_problem_size():
+    """The workspace query runs the same planner as the launch (148 SMs / B200 cluster capacities as defaults without a
+    GPU).  3x3 forward with TMA-addressable rows (W % 8 == 0): dual-slot kernel, scratch = status word + two round
+    parities x CTAs x two slots of 16-byte-slot inboxes; other widths: the single-tile kernel (hardware clusters need no
+    scratch, stream mode one inbox per tile); the blocked 5x5 path two fp32 planes; the fused backward the per-SM history
+    (192 slots x T x 64 x 64 floats)."""
     lib = _lib.load()
+
+    def dual_ws(ctas, p):
+        return 256 + 2 * ctas * 2 * (4 * 8 * p + 4 * 2 * 32) * 16
+
+    plan = _lib.forward_plan(8, 1, 228, 304, 24)                      # headline: 8 images x 35 tiles of 64x40, one round
+    assert plan == dict(kernel=_lib.KERNEL_DUAL, rows_per_warp=5, cx=5, cy=7, ntx=1, nty=1, ctas=140, rounds=1, units_per_class=4, units=8)
+    assert lib.cspn_fwd_workspace_bytes(8, 1, 228, 304, 24, 3, 0) >= dual_ws(140, 5)
+    plan = _lib.forward_plan(32, 1, 352, 1216, 24)                    # KITTI: half images of 21x7 tiles of 64x32, a round per image
+    assert (plan["kernel"], plan["rows_per_warp"], plan["ntx"] * plan["nty"], plan["rounds"]) == (_lib.KERNEL_DUAL, 4, 2, 32)
+    assert 140 <= plan["cx"] * plan["cy"] == plan["ctas"] <= 148
+    assert lib.cspn_fwd_workspace_bytes(32, 1, 352, 1216, 24, 3, 0) >= dual_ws(plan["ctas"], 4)
+    plan = _lib.forward_plan(1, 1, 1080, 1440, 24)                    # one image larger than the GPU: resident units with margins
+    assert plan["kernel"] == _lib.KERNEL_DUAL and plan["cx"] * plan["cy"] <= 148 and plan["ntx"] * plan["nty"] > 1
+    assert _lib.forward_plan(3, 1, 97, 131, 24)["kernel"] == _lib.KERNEL_SINGLE          # odd width: plain-load prologue kernel
+    assert _lib.forward_plan(16, 1, 480, 640, 12, 5, 1)["kernel"] == _lib.KERNEL_BLOCKED
+    assert _lib.forward_plan(1, 1, 20, 30, 4, 7, 1)["kernel"] == _lib.KERNEL_GENERIC
     inbox = (4 * 80 + 4 * 2 * 32) * 16
-    assert lib.cspn_fwd_workspace_bytes(1, 1, 228, 304, 24, 3, 0) == 0                 # one 5x3 cluster: DSMEM
-    assert lib.cspn_fwd_workspace_bytes(7, 1, 228, 304, 24, 3, 0) == 0                 # 7 clusters of 15 fit at once
-    assert lib.cspn_fwd_workspace_bytes(8, 1, 228, 304, 24, 3, 0) == 8 * 15 * inbox    # the 8th would not: stream mode, 120 tiles
-    assert lib.cspn_fwd_workspace_bytes(32, 1, 352, 1216, 24, 3, 0) == 0               # KITTI batch: 4x2 hardware clusters
-    assert lib.cspn_fwd_workspace_bytes(8, 1, 64, 64, 24, 3, 0) == 0                   # single-tile images
+    assert lib.cspn_fwd_workspace_bytes(1, 1, 228, 302, 24, 3, 0) == 0                 # single-tile kernel, one 5x3 cluster: DSMEM
+    assert lib.cspn_fwd_workspace_bytes(8, 1, 228, 302, 24, 3, 0) == 8 * 15 * inbox    # the 8th cluster would not fit: stream mode
     assert lib.cspn_fwd_workspace_bytes(16, 1, 480, 640, 12, 5, 1) == 2 * 16 * 480 * 640 * 4
     assert lib.cspn_fwd_workspace_bytes(16, 1, 480, 640, 4, 5, 1) == 0                 # one launch: no hand-over planes
     hist = 192 * 24 * 64 * 64 * 4

@@ -261,17 +261,89 @@ def test_fused_backward_iteration_counts(iters):
     _check_backward(1, 8, (1, 70, 200), iters, seed=iters + 100, density=None if iters == 3 else 0.05)
 
 
-@pytest.mark.parametrize("exchange", ["global", "dsmem"])
+@pytest.mark.parametrize("exchange", ["global", "dsmem", "auto"])
 def test_forced_exchange_modes(exchange):
-    """Both halo transports of the fused kernels on the same problems (the override is per process, hence the worker):
-    stream mode with several tiles per persistent CTA, hardware clusters with several cluster tiles per image."""
+    """Both halo transports of the single-tile fused kernels (forward with CSPN_FWD_KERNEL=single, and the backward) on
+    the same problems, fp32 and fp16 (the overrides are per process, hence the worker): stream mode with several tiles
+    per persistent CTA, hardware clusters with several cluster tiles per image.  "auto" runs the same worker with the
+    default planner, i.e. the dual-slot forward kernel wherever the guidance is TMA-addressable."""
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, CSPN_EXCHANGE=exchange)
-    r = subprocess.run([sys.executable, os.path.join(root, "tests", "exchange_modes_worker.py")], env=env, capture_output=True, text=True, timeout=600)
+    env = dict(os.environ)
+    if exchange != "auto":
+        env.update(CSPN_EXCHANGE=exchange, CSPN_FWD_KERNEL="single")
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "exchange_modes_worker.py")], env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok " + exchange), r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def _fp16_case(seed, b, cg, h, w, density):
+    g, d, s = make_inputs(seed, b, cg, 1, h, w, density=density)
+    g16, d16, s16 = (a.astype(np.float16) for a in (g, d, s))
+    go16 = np.random.default_rng(seed + 1).standard_normal(d.shape).astype(np.float16)
+    return g16, d16, s16, go16
+
+
+# BASELINE configs[2] at its own precision and size: fp16 storage, fp32 arithmetic, KITTI-shape images (stream /
+# dual-slot forward with 147 tiles per half image, backward in stream mode with 132 tiles per image), and the NYU batch.
+# Oracle: the C restatement in fp32 on the fp16-rounded inputs (SURVEY.md 8d cfg3).  Tolerance: forward 1 fp16 ulp of the
+# output (2^-10 relative) + 1e-4; gradients 1 fp16 ulp of the element + 1e-4 of the largest entry.
+@pytest.mark.parametrize("b,cg,h,w", [(2, 8, 352, 1216), (2, 12, 352, 1216), (8, 8, 228, 304)])
+def test_fp16_full_size_forward_backward_vs_oracle(b, cg, h, w):
+    g16, d16, s16, go16 = _fp16_case(b * h + cg, b, cg, h, w, 0.05 if h == 352 else 0.0072)
+    f32 = [a.astype(np.float32) for a in (g16, d16, s16, go16)]
+    y, tg, td = _run(0, g16, d16, s16, 24, requires_grad=True, dtype=torch.float16)
+    assert _lib.load().cspn_last_path() == _lib.PATH_FUSED and _lib.load().cspn_last_launch_count() == 1
+    ref = c_oracle.forward(f32[0], f32[1], f32[2], 24, 3, 0, threads=0)
+    err = np.abs(y.detach().float().cpu().numpy() - ref)
+    assert (err <= np.abs(ref) * 2.0 ** -10 + FWD_ATOL).all(), f"fp16 forward {b}x{h}x{w} cg {cg}: max err {err.max():.3e}"
+    y.backward(_cu(go16, torch.float16))
+    assert _lib.load().cspn_last_path() == _lib.PATH_FUSED and _lib.load().cspn_last_launch_count() == 1
+    gg, gd = c_oracle.backward(f32[0], f32[1], f32[2], f32[3], 24, 3, 0, threads=0)
+    for got, want, what in ((td.grad, gd, "grad_depth"), (tg.grad, gg, "grad_guidance")):
+        e = np.abs(got.float().cpu().numpy() - want)
+        tol = np.abs(want) * 2.0 ** -10 + GRAD_RTOL * max(1.0, np.abs(want).max())
+        assert (e <= tol).all(), f"fp16 {what} {b}x{h}x{w} cg {cg}: max err {e.max():.3e} (max |ref| {np.abs(want).max():.3e})"
+    if cg > 8:
+        assert torch.count_nonzero(tg.grad[:, 8:]) == 0
+
+
+# One image with more tiles than the GPU has SMs (ADVICE r1: the old persistent stream deadlocked on these because
+# every tile of an image advances in lockstep): the forward cuts them into resident units, the backward runs hardware
+# clusters with margins.  Both must finish and match the oracle.
+@pytest.mark.parametrize("h,w", [(720, 1280), (1080, 1440)])
+def test_single_image_larger_than_the_gpu(h, w):
+    g, d, s = make_inputs(h + w, 1, 8, 1, h, w, density=0.01)
+    go = np.random.default_rng(h).standard_normal(d.shape).astype(np.float32)
+    y, tg, td = _run(0, g, d, s, 24, requires_grad=True)
+    assert _lib.load().cspn_last_path() == _lib.PATH_FUSED
+    ref = c_oracle.forward(g, d, s, 24, 3, 0, threads=0)
+    assert torch.isfinite(y).all()
+    assert_close_nan(y.detach().cpu().numpy(), ref, FWD_ATOL, f"forward 1x{h}x{w}")
+    y.backward(_cu(go))
+    assert _lib.load().cspn_last_path() == _lib.PATH_FUSED
+    gg, gd = c_oracle.backward(g, d, s, go, 24, 3, 0, threads=0)
+    assert torch.isfinite(td.grad).all() and torch.isfinite(tg.grad).all()
+    assert_close_nan(td.grad.cpu().numpy(), gd, GRAD_RTOL * max(1.0, np.abs(gd).max()), f"grad_depth 1x{h}x{w}")
+    assert_close_nan(tg.grad.cpu().numpy(), gg, GRAD_RTOL * max(1.0, np.abs(gg).max()), f"grad_guidance 1x{h}x{w}")
+
+
+# The dual-slot forward kernel over what its planner produces: one unit (single slot, exposed refresh), odd unit counts
+# (last CTAs with one slot), several rounds, units cut with margins, mode OURS, fp16, several depth channels, no sparse.
+@pytest.mark.parametrize("mode,b,c,h,w,iters,density", [
+    (0, 1, 1, 228, 304, 24, 0.0072), (0, 7, 1, 228, 304, 24, 0.0072), (0, 19, 1, 228, 304, 24, 0.0072),
+    (1, 5, 1, 228, 304, 24, 0.02), (0, 3, 1, 352, 1216, 24, 0.05), (1, 1, 1, 480, 640, 24, 0.02),
+    (0, 2, 3, 120, 200, 9, 0.05), (0, 2, 1, 100, 72, 1, 0.05), (0, 2, 1, 100, 72, 2, 0.05), (0, 3, 1, 100, 136, 7, None),
+    (0, 40, 1, 96, 128, 5, 0.05), (1, 2, 1, 64, 64, 40, 0.05),
+])
+def test_dual_slot_forward_planner_grid(mode, b, c, h, w, iters, density):
+    g, d, s = make_inputs(b * h + w + iters, b, 8, c, h, w, density=density)
+    tg, td, ts = _cu(g), _cu(d), _cu(s)
+    y = cspn_new.AffinityPropagate(iters, 3)(tg, td, ts) if mode == 0 else cspn_ours.AffinityPropagate(prop_time=iters)(td, tg, sparse_depth=ts)
+    assert _lib.load().cspn_last_path() == _lib.PATH_FUSED and _lib.load().cspn_last_launch_count() == 1
+    ref = c_oracle.forward(g, d, s, iters, 3, mode, threads=0)
+    assert_close_nan(y.cpu().numpy(), ref, _atol(ref), f"dual mode {mode} {b}x{c}x{h}x{w} T {iters}")
 
 
 # ---- size-independent properties at BASELINE.json's full sizes -------------------------------
