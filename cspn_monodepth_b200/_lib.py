@@ -29,6 +29,10 @@ SIGNATURES = {
     "cspn_bwd_f16": (_c_int, [_c_vp, _c_vp, _c_i64, _c_int, _c_vp, _c_vp, _c_int, _c_vp, _c_vp] + [_c_int] * 7 + [_c_vp, _c_sz, _c_vp]),
     "cspn_fwd_host_f32": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_int, _c_vp] + [_c_int] * 7 + [_c_vp]),
     "cspn_fwd_host_f16": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_int, _c_vp] + [_c_int] * 7 + [_c_vp]),
+    "cspn_fwd_host_submit_f32": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_int, _c_vp] + [_c_int] * 7 + [ctypes.POINTER(_c_int)]),
+    "cspn_fwd_host_submit_f16": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_int, _c_vp] + [_c_int] * 7 + [ctypes.POINTER(_c_int)]),
+    "cspn_host_wait": (_c_int, [_c_int]),
+    "cspn_host_pipeline_depth": (_c_int, []),
 }
 
 PATH_AUTO, PATH_GENERIC, PATH_FUSED, PATH_BLOCKED = 0, 1, 2, 3

@@ -220,6 +220,110 @@ int forward_host_impl(const T* guidance, int64_t gbs, const T* depth, const T* s
     return (int)e3;
 }
 
+
+// ---- pipelined host entry points --------------------------------------------------------------------------------------
+// Per host thread and device: a ring of kPipeDepth slots, each with its own stream, persistent device buffers (grown on
+// demand, never shrunk) and a pinned status word.  A submitted call runs H2D -> kernel -> D2H on its slot's stream, so the
+// H2D copy of call i+1 overlaps the kernel and the D2H copy of call i (PCIe is full duplex, the copy engines are
+// independent of the SMs).  The synchronous cspn_fwd_host_* are kept as they were (they honour the caller's stream).
+constexpr int kPipeDepth = 3;
+struct PipeSlot {
+    cudaStream_t stream; cudaEvent_t done; char* dev; size_t cap; int* status_host; int rc; bool busy; int ticket;
+};
+struct HostPipe { bool ok; PipeSlot slot[kPipeDepth]; int next_ticket; };
+
+HostPipe* host_pipe()
+{
+    static thread_local HostPipe pipes[16] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) { cudaGetLastError(); return nullptr; }
+    HostPipe& hp = pipes[dev];
+    if (!hp.ok) {
+        bool good = true;
+        for (int i = 0; good && i < kPipeDepth; ++i) {
+            PipeSlot& sl = hp.slot[i];
+            sl = PipeSlot{};
+            good = cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking) == cudaSuccess &&
+                   cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming | cudaEventBlockingSync) == cudaSuccess &&
+                   cudaHostAlloc((void**)&sl.status_host, 64, cudaHostAllocDefault) == cudaSuccess;
+        }
+        if (!good) { cudaGetLastError(); return nullptr; }
+        hp.next_ticket = 1;
+        hp.ok = true;
+    }
+    return &hp;
+}
+
+int pipe_wait_slot(PipeSlot& sl)
+{
+    if (!sl.busy) return CSPN_OK;
+    const cudaError_t e = cudaEventSynchronize(sl.done);
+    sl.busy = false;
+    if (sl.rc != CSPN_OK) return sl.rc;
+    if (e != cudaSuccess) return (int)e;
+    return *sl.status_host ? CSPN_ERR_EXCHANGE_TIMEOUT : CSPN_OK;
+}
+
+template <typename T>
+int forward_host_submit_impl(const T* guidance, int64_t gbs, const T* depth, const T* sparse, int sparse_channels, T* out,
+                             int B, int C, int H, int W, int iters, int ksize, int mode, int* ticket)
+{
+    if (ticket) *ticket = 0;
+    TapTable tt;
+    int rc = validate_common(guidance, gbs, depth, sparse, sparse_channels, B, C, H, W, iters, ksize, mode, &tt);
+    if (rc != CSPN_OK) return rc;
+    if (!ticket) return CSPN_ERR_NULL_POINTER;
+    if (B == 0) return CSPN_OK;                       // ticket 0: nothing to wait for
+    if (!out) return CSPN_ERR_NULL_POINTER;
+    HostPipe* hp = host_pipe();
+    if (!hp) return (int)cudaErrorInitializationError;
+    const int tk = hp->next_ticket++;
+    PipeSlot& sl = hp->slot[tk % kPipeDepth];
+    pipe_wait_slot(sl);                               // back-pressure: the call that used this slot kPipeDepth submits ago (its status is dropped)
+    const size_t hw = (size_t)H * W;
+    const size_t g_img = (size_t)tt.n * hw * sizeof(T);
+    const size_t g_bytes = (size_t)B * g_img, d_bytes = (size_t)B * C * hw * sizeof(T);
+    const size_t s_bytes = sparse ? (size_t)B * sparse_channels * hw * sizeof(T) : 0;
+    const size_t ws_bytes = cspn_fwd_workspace_bytes(B, C, H, W, iters, ksize, mode);
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t total = up(g_bytes) + 2 * up(d_bytes) + up(s_bytes) + up(ws_bytes) + 256;
+    if (sl.cap < total) {
+        if (sl.dev) cudaFree(sl.dev);
+        sl.dev = nullptr; sl.cap = 0;
+        const cudaError_t e = cudaMalloc((void**)&sl.dev, total);
+        if (e != cudaSuccess) return (int)e;
+        sl.cap = total;
+    }
+    char* q = sl.dev;
+    T* dg = (T*)q; q += up(g_bytes);
+    T* dd = (T*)q; q += up(d_bytes);
+    T* dout = (T*)q; q += up(d_bytes);
+    T* ds = sparse ? (T*)q : nullptr; q += up(s_bytes);
+    void* dws = (void*)q;
+    // the dual-slot kernel reports an exchange timeout through the first int of its workspace (device buffers are aligned,
+    // so a dual-slot plan is what runs); other kernels have no such word
+    const bool has_status = iters > 0 && use_fused(B, C, H, W, iters, ksize, mode, nullptr) && dual_supported(B, C, H, W, iters, ksize, mode);
+    *sl.status_host = 0;
+    cudaError_t e = cudaSuccess;
+    {
+        if (gbs == (int64_t)tt.n * (int64_t)hw) e = cudaMemcpyAsync(dg, guidance, g_bytes, cudaMemcpyHostToDevice, sl.stream);
+        else e = cudaMemcpy2DAsync(dg, g_img, guidance, (size_t)gbs * sizeof(T), g_img, (size_t)B, cudaMemcpyHostToDevice, sl.stream);
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dd, depth, d_bytes, cudaMemcpyHostToDevice, sl.stream);
+    if (e == cudaSuccess && sparse) e = cudaMemcpyAsync(ds, sparse, s_bytes, cudaMemcpyHostToDevice, sl.stream);
+    rc = CSPN_OK;
+    if (e == cudaSuccess) {
+        rc = forward_impl<T>(dg, (int64_t)tt.n * (int64_t)hw, dd, ds, sparse_channels, dout, B, C, H, W, iters, ksize, mode, dws, ws_bytes + 256, sl.stream);
+        if (rc == CSPN_OK) e = cudaMemcpyAsync(out, dout, d_bytes, cudaMemcpyDeviceToHost, sl.stream);
+        if (rc == CSPN_OK && e == cudaSuccess && has_status) e = cudaMemcpyAsync(sl.status_host, dws, 4, cudaMemcpyDeviceToHost, sl.stream);
+    }
+    const cudaError_t e2 = cudaEventRecord(sl.done, sl.stream);
+    sl.rc = rc != CSPN_OK ? rc : (e != cudaSuccess ? (int)e : (int)e2);
+    sl.busy = true; sl.ticket = tk;
+    *ticket = tk;
+    return sl.rc;
+}
+
 }  // namespace
 }  // namespace cspn
 
@@ -241,6 +345,7 @@ const char* cspn_error_string(int code)
         case CSPN_ERR_WORKSPACE: return "cspn: workspace missing or smaller than cspn_*_workspace_bytes()";
         case CSPN_ERR_BAD_SPARSE_CHANNELS: return "cspn: sparse must have 1 or C channels";
         case CSPN_ERR_ALIAS: return "cspn: out aliases an input";
+        case CSPN_ERR_EXCHANGE_TIMEOUT: return "cspn: a tile never received its neighbours' halo (kernel not co-resident?); the output is NaN-filled";
         default: break;
     }
     if (code > 0) return cudaGetErrorString((cudaError_t)code);
@@ -323,6 +428,28 @@ int cspn_fwd_host_f32(const float* guidance, int64_t gbs, const float* depth, co
 {
     return forward_host_impl<float>(guidance, gbs, depth, sparse, sparse_channels, out, B, C, H, W, iters, ksize, mode, stream);
 }
+int cspn_fwd_host_submit_f32(const float* guidance, int64_t gbs, const float* depth, const float* sparse, int sparse_channels,
+                             float* out, int B, int C, int H, int W, int iters, int ksize, int mode, int* ticket)
+{
+    return forward_host_submit_impl<float>(guidance, gbs, depth, sparse, sparse_channels, out, B, C, H, W, iters, ksize, mode, ticket);
+}
+int cspn_fwd_host_submit_f16(const void* guidance, int64_t gbs, const void* depth, const void* sparse, int sparse_channels,
+                             void* out, int B, int C, int H, int W, int iters, int ksize, int mode, int* ticket)
+{
+    return forward_host_submit_impl<__half>((const __half*)guidance, gbs, (const __half*)depth, (const __half*)sparse, sparse_channels,
+                                            (__half*)out, B, C, H, W, iters, ksize, mode, ticket);
+}
+int cspn_host_wait(int ticket)
+{
+    if (ticket <= 0) return CSPN_OK;
+    HostPipe* hp = host_pipe();
+    if (!hp) return (int)cudaErrorInitializationError;
+    PipeSlot& sl = hp->slot[ticket % kPipeDepth];
+    if (!sl.busy || sl.ticket != ticket) return CSPN_OK;      // already waited for (or retired by a later submit)
+    return pipe_wait_slot(sl);
+}
+int cspn_host_pipeline_depth(void) { return kPipeDepth; }
+
 int cspn_fwd_host_f16(const void* guidance, int64_t gbs, const void* depth, const void* sparse, int sparse_channels,
                       void* out, int B, int C, int H, int W, int iters, int ksize, int mode, void* stream)
 {

@@ -26,7 +26,20 @@
 namespace cspn {
 namespace {
 
-constexpr int kDNW = 8;                      // warps per CTA; the tile is 64 x (8 * P) pixels per slot
+// Optional cycle trace (build with CSPN_TRACE=1): lane 0 of every warp stamps clock64() at fixed points (tools/trace_dual.py).
+#ifdef CSPN_TRACE
+__device__ long long* g_dtrace = nullptr;
+constexpr int kDTraceSlots = 128;
+#define DTRACE(slot) do { if (g_dtrace && (threadIdx.x & 31) == 0) g_dtrace[((size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kDTraceSlots + (slot)] = clock64(); } while (0)
+#else
+#define DTRACE(slot) do { } while (0)
+#endif
+
+constexpr int kSW = 4;                       // compute warps per slot: the slot's tile is 64 x (4 * P) pixels
+constexpr int kDNW = 2 * kSW;                // compute warps per CTA: warps 0-3 = slot A, 4-7 = slot B
+constexpr int kCommWarps = 4;                // one warp group: warps 8, 10 serve slot A, warps 9, 11 slot B
+constexpr int kDThreads = (kDNW + kCommWarps) * 32;
+constexpr int kRegsCompute = 232, kRegsComm = 40;      // setmaxnreg: 256 x 232 + 128 x 40 = 384 x 168 registers
 constexpr uint32_t kNone = 0xffffffffu;
 constexpr int kSpinLimit = 1 << 20;
 
@@ -45,17 +58,35 @@ struct DualParams {
     int nA;                  // units per class and round
     int total_units;         // planes * ntx * nty
     int rounds;
-    uint4* inbox;            // [2 round parities][grid][2 slots] inboxes of InboxGeom<TH>::size uint4
+    uint4* inbox;            // [2 round parities][grid][2 slots][2 refresh parities][Msg::n] messages of 16 bytes
     uint32_t tag_base;       // tag of refresh e in round r is tag_base + 64 r + e (never 0)
     int* status;             // set to 1 when a neighbour never showed up (output is NaN-filled as well)
 };
 
+// Messages of one tile and refresh, in the order of the RECEIVER's halo ring:
+//   [0, TH)            left halo column  (rows of the tile)      <- left neighbour's rim column (its lane 30)
+//   [TH, 2TH)          right halo column                          <- right neighbour's rim column (its lane 1)
+//   [2TH, 2TH+64)      top halo rows 0,1 (32 lanes each)          <- upper neighbour's rim rows TH-4, TH-3; lane 0 / 31 from the
+//   [2TH+64, 2TH+128)  bottom halo rows TH-2, TH-1                   diagonal neighbours when there is a left / right neighbour
+// The sender stages its rim in the same order (left rim column, right rim column, top rim rows 2,3, bottom rim rows).
+template <int P> struct Msg {
+    static constexpr int TH = kSW * P;
+    static constexpr int n = 2 * TH + 4 * 32;
+    static constexpr int K = (n + 31) / 32;          // 32-message groups; the two communication warps of a slot take every other one
+    static constexpr int KH = (K + 1) / 2;
+    static constexpr uint32_t inbox = 2 * n;         // uint4 per tile: two refresh parities
+};
+
 template <int P>
 struct __align__(128) DualSm {
-    float rowbuf[2][2][kDNW][2][kTileW];     // [slot][step parity][warp][first / last row of the warp's strip][x]
-    uint4 colz[2][2][kDNW * P];              // landing zone of the halo columns: [slot][side: left, right][tile row]
-    uint4 rowz[2][2][kHaloY][32];            // landing zone of the halo rows:    [slot][side: top, bottom][row][lane]
+    float rowbuf[2][2][kSW][2][kTileW];      // [slot][step parity][warp][first / last row of the warp's strip][x]
+    u64 stage[2][Msg<P>::n];                 // outgoing rim of slot s (compute warps -> communication warps)
+    u64 land[2][Msg<P>::n];                  // incoming halo ring of slot s (communication warps -> compute warps)
     u64 tma_bar[2][8];
+    u64 row_bar[2][2];                       // [slot][step parity]: the slot's 4 compute warps have published their edge rows
+    u64 rim_bar[2];                          // slot s: the rim is staged (4 arrivals, one per compute warp)
+    u64 halo_bar[2];                         // slot s: the halo ring has landed (2 arrivals, one per communication warp)
+    int poison;
 };
 
 __device__ __forceinline__ u64 pk_bits(uint32_t lo, uint32_t hi)
@@ -64,32 +95,162 @@ __device__ __forceinline__ u64 pk_bits(uint32_t lo, uint32_t hi)
     asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
     return d;
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void slot_bar_sync(int s)      // the 4 compute warps of slot s (barrier 0 = __syncthreads is CTA-wide)
+{
+    asm volatile("bar.sync %0, %1;" :: "r"(1 + s), "n"(kSW * 32) : "memory");
+}
+
+// ---- communication warp `half` (0 / 1) of slot s: ships the staged rim to the neighbours' inboxes and polls this tile's
+// inbox; the two warps of a slot split the 32-message groups (even / odd) ----------------------------------------------
+template <typename T, int P>
+__device__ __forceinline__ void comm_role(const DualParams<T>& p, DualSm<P>& sm, const int s, const int half, const int lane)
+{
+    using M = Msg<P>;
+    constexpr int TH = M::TH;
+    const int w = blockIdx.x;
+    const int uidx = w / p.per_unit, within = w - uidx * p.per_unit;
+    const int ccy = within / p.cx, ccx = within - ccy * p.cx;
+    const bool hasL = ccx > 0, hasR = ccx < p.cx - 1, hasU = ccy > 0, hasD = ccy < p.cy - 1;
+    if (p.per_unit <= 1) return;                              // single-tile units exchange nothing
+    const int E = (p.iters + 1) / 2 - 1;                      // refreshes per round
+    if (E <= 0) return;
+
+    // per-lane message tables (refresh parity 0, round parity 0): where staged message k * 32 + lane goes, and whether
+    // inbox entry k * 32 + lane is expected
+    uint32_t dst[M::KH];
+    uint32_t need = 0u;
+#pragma unroll
+    for (int j = 0; j < M::KH; ++j) {
+        const int k = 2 * j + half;
+        const int idx = k * 32 + lane;
+        dst[j] = kNone;
+        int nb = -1, in_idx = 0;
+        if (k >= M::K) continue;
+        if (idx < TH) { if (hasL) { nb = w - 1; in_idx = TH + idx; need |= 1u << j; } }
+        else if (idx < 2 * TH) { if (hasR) { nb = w + 1; in_idx = idx - TH; need |= 1u << j; } }
+        else if (idx < M::n) {
+            const int q = idx - 2 * TH, bottom = q >> 6, l = q & 31;
+            const bool own = !(l == 0 && hasL) && !(l == 31 && hasR);
+            if (!bottom) { if (hasU) { need |= 1u << j; if (own) { nb = w - p.cx; in_idx = 2 * TH + 64 + (q & 63); } } }
+            else { if (hasD) { need |= 1u << j; if (own) { nb = w + p.cx; in_idx = 2 * TH + (q & 63); } } }
+        }
+        if (nb >= 0) dst[j] = (uint32_t)(nb * 2 + s) * M::inbox + (uint32_t)in_idx;
+    }
+    // corners (warp `half` 1): lanes 0..7 = (top / bottom rim rows) x (left / right rim lane) x (row h) -> diagonal neighbour's corner lane
+    uint32_t cdst = kNone, csrc = 0u;
+    if (half == 1 && lane < 8) {
+        const bool bottom = lane & 4, right = lane & 2; const int h = lane & 1;
+        if ((bottom ? hasD : hasU) && (right ? hasR : hasL)) {
+            const int nb = w + (bottom ? p.cx : -p.cx) + (right ? 1 : -1);
+            csrc = (uint32_t)(2 * TH + (bottom ? 64 : 0) + h * 32 + (right ? 30 : 1));
+            cdst = (uint32_t)(nb * 2 + s) * M::inbox + (uint32_t)(2 * TH + (bottom ? 0 : 64) + h * 32 + (right ? 0 : 31));
+        }
+    }
+
+    uint32_t rim_phase = 0u;
+    bool poisoned = false;
+    for (int r = 0; r < p.rounds; ++r) {
+        const int first = r * 2 * p.nA;
+        const int n = min(p.total_units - first, 2 * p.nA);
+        const int nAr = (n + 1) >> 1;
+        if (uidx >= nAr) break;
+        if (s == 1 && uidx >= n - nAr) break;               // no slot B in this (last) round
+        uint4* const set_base = p.inbox + (size_t)(r & 1) * gridDim.x * 2u * M::inbox;
+        uint4* const my_box = set_base + (size_t)(w * 2 + s) * M::inbox;
+        const uint32_t round_tag = p.tag_base + ((uint32_t)r << 6);
+        for (int e1 = 1; e1 <= E; ++e1) {
+            const uint32_t tag = round_tag + (uint32_t)e1;
+            const uint32_t par_off = (uint32_t)(e1 & 1) * M::n;
+            // ---- ship: the compute warps have staged the rim of refresh e1 ----
+            mbar_wait(smem_u32(&sm.rim_bar[s]), rim_phase);
+            rim_phase ^= 1u;
+#pragma unroll
+            for (int j = 0; j < M::KH; ++j)
+                if (dst[j] != kNone) st_ll(set_base + dst[j] + par_off, sm.stage[s][(2 * j + half) * 32 + lane], tag);
+            if (cdst != kNone) st_ll(set_base + cdst + par_off, sm.stage[s][csrc], tag);
+            // ---- poll: the neighbours' rims of the same refresh (they ship at about the same time: the first look would
+            // always come too early, so it is delayed by roughly one store latency) ----
+            const uint4* box = my_box + par_off + half * 32 + lane;
+            uint4 q[M::KH];
+#pragma unroll
+            for (int j = 0; j < M::KH; ++j)
+                if (need >> j & 1u) q[j] = ld_ll(box + j * 64);
+            for (int spin = 0;; ++spin) {
+                bool ok = true;
+#pragma unroll
+                for (int j = 0; j < M::KH; ++j)
+                    if ((need >> j & 1u) && !(q[j].y == tag && q[j].w == tag)) { ok = false; q[j] = ld_ll(box + j * 64); }
+                if (__all_sync(0xffffffffu, ok)) break;
+                if (spin > kSpinLimit || poisoned) { poisoned = true; break; }      // neighbours never showed up: fail loudly, do not hang
+            }
+#pragma unroll
+            for (int j = 0; j < M::KH; ++j)
+                if (need >> j & 1u) sm.land[s][(2 * j + half) * 32 + lane] = pk_bits(q[j].x, q[j].z);
+            if (poisoned) sm.poison = 1;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&sm.halo_bar[s]));
+        }
+        // every message addressed to this tile in this round has been consumed: leave the inbox clean for the round after
+        // next / the next launch / graph replay
+        // (each warp cleans exactly the entries it polls: its partner may still be waiting for its own)
+#pragma unroll
+        for (int j = 0; j < M::KH; ++j) {
+            const int idx = (2 * j + half) * 32 + lane;
+            if (idx < M::n) { my_box[idx] = make_uint4(0, 0, 0, 0); my_box[M::n + idx] = make_uint4(0, 0, 0, 0); }
+        }
+        __threadfence();
+    }
+    if (poisoned && p.status && lane == 0) *p.status = 1;
+}
 
 template <typename T, int P, int MODE>
-__global__ void __launch_bounds__(kDNW * 32, 1)
+__global__ void __launch_bounds__(kDThreads, 1)
 dual3x3_kernel(const __grid_constant__ DualParams<T> p, const __grid_constant__ CUtensorMap gmap)
 {
-    constexpr int NW = kDNW, TH = NW * P, STEPY = TH - 2 * kHaloY;
+    constexpr int TH = kSW * P, STEPY = TH - 2 * kHaloY;
     static_assert(P >= 4, "rim rows 2,3 / P-4,P-3 must live in the first / last warp");
     using St = Stage<T, TH, MODE>;
-    using IB = InboxGeom<TH>;
     typedef typename std::conditional<sizeof(T) == 4, float2, __half2>::type V2;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     DualSm<P>& sm = *reinterpret_cast<DualSm<P>*>(smem_raw);
     constexpr size_t kStageOff = (sizeof(DualSm<P>) + 127) & ~(size_t)127;
-    T* const stage_base = reinterpret_cast<T*>(smem_raw + kStageOff);                 // slot s: + s * 8 * St::plane
-    u64* const ctile_base = reinterpret_cast<u64*>(smem_raw + kStageOff);            // aliases the staging buffer of its slot
-    constexpr size_t kSlotStageBytes = St::bytes;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    DTRACE(0);
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int s = 0; s < 2; ++s)
+        for (int s = 0; s < 2; ++s) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) mbar_init(smem_u32(&sm.tma_bar[s][k]), 1);
+            mbar_init(smem_u32(&sm.row_bar[s][0]), kSW);
+            mbar_init(smem_u32(&sm.row_bar[s][1]), kSW);
+            mbar_init(smem_u32(&sm.rim_bar[s]), kSW);
+            mbar_init(smem_u32(&sm.halo_bar[s]), 2);
+        }
+        sm.poison = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (blockIdx.x == 0 && p.status) *p.status = 0;      // a timeout (2^20 polls later at the earliest) sets it to 1
     }
     __syncthreads();
+
+    if (warp >= kDNW) {
+        // ===== communication warp group: hands its registers to the compute warps =====
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(kRegsComm));
+        comm_role<T, P>(p, sm, (warp - kDNW) & 1, (warp - kDNW) >> 1, lane);
+        return;
+    }
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(kRegsCompute));
+
+    // ===== compute warps: warp group s owns slot s =====
+    const int s = warp / kSW, wl = warp - s * kSW;           // slot, warp within the slot's tile
+    T* const stage = reinterpret_cast<T*>(smem_raw + kStageOff + (size_t)s * St::bytes);
+    // The re-injection term c lives where the guidance was staged (read once per row and step; every thread only re-reads
+    // its own words).
+    u64* const ctile = reinterpret_cast<u64*>(smem_raw + kStageOff + (size_t)s * St::bytes) + (wl * P) * 32 + lane;
 
     // ---- position of this CTA's tiles inside their units (the same for both slots) ------------------------------
     const int w = blockIdx.x;
@@ -100,121 +261,72 @@ dual3x3_kernel(const __grid_constant__ DualParams<T> p, const __grid_constant__ 
     const int H = p.H, W = p.W;
     const size_t hw = (size_t)H * W;
 
-    // Outgoing messages of this lane, as uint4 offsets from (inbox set base + slot * IB::size), refresh parity 0:
-    //   col_dst  lanes 1 / 30: my rim column, all P rows of the warp -> left neighbour's right box / right neighbour's left box
-    //   row_dst  first / last warp: my rim rows (2,3 / TH-4,TH-3) -> upper neighbour's bottom box / lower neighbour's top box,
-    //            except the lanes whose pixels I do not own (lane 0 / 31 next to a left / right neighbour)
-    //   diag_dst first / last warp, lanes 1 / 30: the same rim rows -> the corner lane (31 / 0) of the DIAGONAL neighbour's box
-    uint32_t col_dst = kNone, row_dst = kNone, diag_dst = kNone;
-    if (multi) {
-        const uint32_t slot2 = 2u * IB::size;
-        if (lane == 1 && hasL) col_dst = (uint32_t)(w - 1) * slot2 + IB::col_side + (uint32_t)(warp * P);
-        if (lane == 30 && hasR) col_dst = (uint32_t)(w + 1) * slot2 + (uint32_t)(warp * P);
-        const bool own = !(lane == 0 && hasL) && !(lane == 31 && hasR);
-        if (warp == 0 && hasU) {
-            const uint32_t up = (uint32_t)(w - p.cx) * slot2 + IB::row_base + IB::row_side;
-            if (own) row_dst = up + (uint32_t)lane;
-            if (lane == 1 && hasL) diag_dst = up - slot2 + 31u;
-            if (lane == 30 && hasR) diag_dst = up + slot2;
-        }
-        if (warp == NW - 1 && hasD) {
-            const uint32_t dn = (uint32_t)(w + p.cx) * slot2 + IB::row_base;
-            if (own) row_dst = dn + (uint32_t)lane;
-            if (lane == 1 && hasL) diag_dst = dn - slot2 + 31u;
-            if (lane == 30 && hasR) diag_dst = dn + slot2;
-        }
-    }
-    // Incoming: what this lane prefetches from the CTA's own inbox (exactly what its warp consumes)
-    const int pf_sd = lane >> 4, pf_row = warp * P + (lane & 15);
-    const bool pf_col = multi && (lane & 15) < P && (pf_sd == 0 ? hasL : hasR);
-    const bool rows_top = multi && warp == 0 && hasU, rows_bot = multi && warp == NW - 1 && hasD;
+    // roles of this lane in the halo exchange (through shared memory only; the communication warps do the rest)
+    const bool rim_l = multi && lane == 1 && hasL, rim_r = multi && lane == 30 && hasR;
+    const bool rim_t = multi && wl == 0 && hasU, rim_b = multi && wl == kSW - 1 && hasD;       // warp-uniform
     const bool edge = multi && ((lane == 0 && hasL) || (lane == 31 && hasR));
-    const int edge_sd = lane == 31 ? 1 : 0;
+    const int edge_off = (lane == 31 ? TH : 0) + wl * P;
 
-    bool poisoned = false;
-    if (blockIdx.x == 0 && threadIdx.x == 0 && p.status) *p.status = 0;     // a timeout (2^20 polls later at the earliest) sets it to 1
+    uint32_t phases = 0u;        // bit par: phase of row_bar[s][par]; bit 2: phase of halo_bar[s]
 
     for (int r = 0; r < p.rounds; ++r) {
-        // ---- which units this CTA serves in round r ------------------------------------------------------------
+        // ---- which unit this slot serves in round r ------------------------------------------------------------
         const int first = r * 2 * p.nA;
         const int n = min(p.total_units - first, 2 * p.nA);
         const int nAr = (n + 1) >> 1;
         if (uidx >= nAr) break;                             // later rounds are never larger
-        const bool haveB = uidx < n - nAr;
-        const int unit_a = first + uidx, unit_b = first + nAr + uidx;
-        const uint32_t set_off = (uint32_t)(r & 1) * gridDim.x * 2u * IB::size;
-        const uint32_t round_tag = p.tag_base + ((uint32_t)r << 6);
-        uint4* const my_box = p.inbox + set_off + (size_t)w * 2u * IB::size;        // slot s: + s * IB::size
-        uint4* const out_base = p.inbox + set_off;
+        if (s == 1 && uidx >= n - nAr) break;               // no slot B in this (last) round
+        const int unit = first + (s ? nAr : 0) + uidx;
 
-        struct Geo { int plane, b, ch, tix, tiy, ox, oy; };
-        auto geo_of = [&](int unit) {
-            Geo g;
-            const int upp = p.ntx * p.nty;
-            g.plane = unit / upp;
-            const int sub = unit - g.plane * upp;
-            g.tiy = sub / p.ntx; g.tix = sub - g.tiy * p.ntx;
-            g.b = g.plane / p.C; g.ch = g.plane - g.b * p.C;
-            g.ox = g.tix * p.stepx + ccx * kStepX;
-            g.oy = g.tiy * p.stepy + ccy * STEPY;
-            return g;
-        };
+        const int upp = p.ntx * p.nty;
+        const int plane = unit / upp, sub = unit - plane * upp;
+        const int tiy = sub / p.ntx, tix = sub - tiy * p.ntx;
+        const int b = plane / p.C, ch = plane - b * p.C;
+        const int ox = tix * p.stepx + ccx * kStepX, oy = tiy * p.stepy + ccy * STEPY;
 
-        if (r) __syncthreads();                             // every warp is done with the previous round's shared memory
+        if (r) slot_bar_sync(s);                            // every warp of the slot is done with the previous round's shared memory
 
-        u64 nwA[P][8], nwB[P][8], A0[P], A1[P];
-        {
-        const Geo ga = geo_of(unit_a), gb = geo_of(haveB ? unit_b : unit_a);
-
-        // ---- TMA: 8 boxes per slot, one per guidance channel, each on its own barrier ---------------------------
-        if (threadIdx.x == 0) {
+        // ---- TMA: one box per guidance channel, each on its own barrier; lane k of the slot's first warp issues box k ----
+        if (wl == 0) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-#pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                if (s == 1 && !haveB) break;
-                const Geo& g = s ? gb : ga;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const uint32_t bar = smem_u32(&sm.tma_bar[s][k]);
-                    mbar_arrive_expect_tx(bar, (uint32_t)St::box_bytes);
-                    tma_load_4d(smem_u32(stage_base + (size_t)s * 8 * St::plane + (size_t)k * St::plane), &gmap, bar, St::box_x(g.ox), g.oy - St::apron, k, g.b);
-                }
+            if (lane < 8) {
+                const uint32_t bar = smem_u32(&sm.tma_bar[s][lane]);
+                mbar_arrive_expect_tx(bar, (uint32_t)St::box_bytes);
+                tma_load_4d(smem_u32(stage + (size_t)lane * St::plane), &gmap, bar, St::box_x(ox), oy - St::apron, lane, b);
             }
         }
+        DTRACE(1);
 
         // ---- prologue: loop-invariant weights n'_j = (1-m) n_j in registers, c = m d0 in shared memory, r^0 = d0 ----
-        u64 ccA[P], ccB[P];
-        V2 dvA[P], svA[P], dvB[P], svB[P];
-        auto load_ds = [&](const Geo& g, V2 (&dv)[P], V2 (&sv)[P]) {
-            const T* db = p.depth + (size_t)g.plane * hw;
-            const T* sb = p.sparse ? p.sparse + ((size_t)g.b * p.sparse_channels + (p.sparse_channels == 1 ? 0 : g.ch)) * hw : nullptr;
-            const int cgx = min(max(g.ox + 2 * lane, 0), W - 2);
-#pragma unroll
-            for (int i = 0; i < P; ++i) {
-                const size_t off = (size_t)min(max(g.oy + warp * P + i, 0), H - 1) * W + cgx;
-                dv[i] = *reinterpret_cast<const V2*>(db + off);
-                if (sb) sv[i] = *reinterpret_cast<const V2*>(sb + off);
-            }
-        };
-        load_ds(ga, dvA, svA);
-        if (haveB) load_ds(gb, dvB, svB);
-
-        auto weights = [&](int s, const Geo& g, const V2 (&dv)[P], const V2 (&sv)[P], u64 (&nw)[P][8], u64 (&A)[P], u64 (&cc)[P]) {
-            const int gx = g.ox + 2 * lane, gy0 = g.oy + warp * P;
+        u64 nw[P][8], A[P];
+        {
+            u64 cc[P];
+            const int gx = ox + 2 * lane, gy0 = oy + wl * P;
             const bool x_in = gx >= 0 && gx < W;           // W is even and gx is even: both pixels of the pair are in or out together
-            const bool has_sparse = p.sparse != nullptr;
+            {
+                V2 dv[P], sv[P];
+                const T* db = p.depth + (size_t)plane * hw;
+                const T* sb = p.sparse ? p.sparse + ((size_t)b * p.sparse_channels + (p.sparse_channels == 1 ? 0 : ch)) * hw : nullptr;
+                const int cgx = min(max(gx, 0), W - 2);
 #pragma unroll
-            for (int i = 0; i < P; ++i) {
-                const int gy = gy0 + i;
-                const bool in = gy >= 0 && gy < H && x_in;
-                const float2 d = to_f32x2(dv[i]);
-                float2 m = make_float2(0.f, 0.f);
-                if (has_sparse) { const float2 sp2 = to_f32x2(sv[i]); m = make_float2(signf(sp2.x), signf(sp2.y)); }
-                A[i] = in ? pk(d.x, d.y) : 0ull;
-                cc[i] = in ? pk(m.x, m.y) : 0ull;           // the mask, until it is folded into the weights below
+                for (int i = 0; i < P; ++i) {
+                    const size_t off = (size_t)min(max(gy0 + i, 0), H - 1) * W + cgx;
+                    dv[i] = *reinterpret_cast<const V2*>(db + off);
+                    if (sb) sv[i] = *reinterpret_cast<const V2*>(sb + off);
+                }
+#pragma unroll
+                for (int i = 0; i < P; ++i) {
+                    const int gy = gy0 + i;
+                    const bool in = gy >= 0 && gy < H && x_in;
+                    const float2 d = to_f32x2(dv[i]);
+                    float2 m = make_float2(0.f, 0.f);
+                    if (sb) { const float2 sp2 = to_f32x2(sv[i]); m = make_float2(signf(sp2.x), signf(sp2.y)); }
+                    A[i] = in ? pk(d.x, d.y) : 0ull;
+                    cc[i] = in ? pk(m.x, m.y) : 0ull;           // the mask, until it is folded into the weights below
+                }
             }
-            const T* stage = stage_base + (size_t)s * 8 * St::plane;
-            const int x_off = g.ox - St::box_x(g.ox);
+            DTRACE(2);
+            const int x_off = ox - St::box_x(ox);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 mbar_wait(smem_u32(&sm.tma_bar[s][k]), (uint32_t)(r & 1));
@@ -225,17 +337,18 @@ dual3x3_kernel(const __grid_constant__ DualParams<T> p, const __grid_constant__ 
                     const int dy = jj / 3 - 1, dx = jj % 3 - 1;
 #pragma unroll
                     for (int i = 0; i < P; ++i) {
-                        const T* src = sp + (warp * P + i + 1 + dy) * St::cols + x_off + 2 * lane + dx;
+                        const T* src = sp + (wl * P + i + 1 + dy) * St::cols + x_off + 2 * lane + dx;
                         nw[i][j] = pk(fabsf(to_f32(src[0])), fabsf(to_f32(src[1])));       // zero-filled outside the image
                     }
                 } else {
 #pragma unroll
                     for (int i = 0; i < P; ++i) {
-                        const T* src = sp + (warp * P + i) * St::cols + x_off + 2 * lane;
+                        const T* src = sp + (wl * P + i) * St::cols + x_off + 2 * lane;
                         nw[i][k] = pk(to_f32(src[0]), to_f32(src[1]));
                     }
                 }
             }
+            DTRACE(3);
             if (MODE == CSPN_MODE_NEW) {
 #pragma unroll
                 for (int i = 0; i < P; ++i) {
@@ -278,185 +391,150 @@ dual3x3_kernel(const __grid_constant__ DualParams<T> p, const __grid_constant__ 
                     cc[i] = mul2(cc[i], A[i]);
                 }
             }
-        };
-        weights(0, ga, dvA, svA, nwA, A0, ccA);
-        if (haveB) weights(1, gb, dvB, svB, nwB, A1, ccB);
+            DTRACE(4);
+            slot_bar_sync(s);                               // every warp of the slot has taken its guidance out of the staging buffer
+#pragma unroll
+            for (int i = 0; i < P; ++i) ctile[i * 32] = cc[i];
+        }
 
-        // The re-injection term lives where the guidance was staged (read once per row and step; every thread only
-        // re-reads its own words).
-        __syncthreads();                                    // every warp has taken its guidance out of the staging buffers
-        {
-            u64* const cA = ctile_base + (warp * P) * 32 + lane;
-            u64* const cB = reinterpret_cast<u64*>(smem_raw + kStageOff + kSlotStageBytes) + (warp * P) * 32 + lane;
+        // ---- one step r'(p) = c(p) + sum_j n'_j(p) r(p + o_j) ------------------------------------------------------
+        // Split-phase row exchange: the warp publishes its edge rows and arrives on the slot's barrier, accumulates
+        // everything that only needs its own rows (148 of the 160 FMAs per thread for P = 10), and only then waits for
+        // the rows of the warps above and below - the barrier latency and the skew between warps hide behind the FMAs.
+        // Within the bulk the FMAs that need no shuffle come first (the centre column and the partner pixel of the pair).
+        auto step = [&](int par) {
+            *reinterpret_cast<u64*>(&sm.rowbuf[s][par][wl][0][2 * lane]) = A[0];
+            *reinterpret_cast<u64*>(&sm.rowbuf[s][par][wl][1][2 * lane]) = A[P - 1];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&sm.row_bar[s][par]));
+            // Source row rr is scattered into output rows rr+1, rr, rr-1.  Its left / right neighbours come from shuffles that
+            // are issued two rows ahead; output row rr-1 is complete after source row rr and replaces the old row in place
+            // (rows 0 and P-1 stay open until the neighbour warps' rows are in).
+            float a0[P], a1[P], l[P], rt[P];
 #pragma unroll
-            for (int i = 0; i < P; ++i) cA[i * 32] = ccA[i];
-            if (haveB) {
-#pragma unroll
-                for (int i = 0; i < P; ++i) cB[i * 32] = ccB[i];
+            for (int i = 0; i < 2 && i < P; ++i) {
+                l[i] = __shfl_up_sync(0xffffffffu, hi_of(A[i]), 1);
+                rt[i] = __shfl_down_sync(0xffffffffu, lo_of(A[i]), 1);
             }
-        }
-        }
-        u64* const ctA = ctile_base + (warp * P) * 32 + lane;
-        u64* const ctB = reinterpret_cast<u64*>(smem_raw + kStageOff + kSlotStageBytes) + (warp * P) * 32 + lane;
-
-        // ---- building blocks of the step loop --------------------------------------------------------------------
-        auto exchange_rows = [&](int s, int par, const u64 (&A)[P], u64& top, u64& bot) {
-            *reinterpret_cast<u64*>(&sm.rowbuf[s][par][warp][0][2 * lane]) = A[0];
-            *reinterpret_cast<u64*>(&sm.rowbuf[s][par][warp][1][2 * lane]) = A[P - 1];
-            __syncthreads();
-            top = 0ull; bot = 0ull;
-            if (warp > 0) top = *reinterpret_cast<const u64*>(&sm.rowbuf[s][par][warp - 1][1][2 * lane]);
-            if (warp < NW - 1) bot = *reinterpret_cast<const u64*>(&sm.rowbuf[s][par][warp + 1][0][2 * lane]);
-        };
-
-        // One step r'(p) = c(p) + sum_j n'_j(p) r(p + o_j), organised by SOURCE row (scalar FMAs on the halves of the
-        // packed pairs; see cspn_fused3x3.cuh compute_step for the derivation), in place.
-        auto sweep = [&](const u64 (&nw)[P][8], u64 (&A)[P], const u64* ctile, u64 top, u64 bot) {
-            float a0[P], a1[P];
+            { const u64 ci = ctile[0]; a0[0] = lo_of(ci); a1[0] = hi_of(ci); }
 #pragma unroll
-            for (int rr = -1; rr <= P; ++rr) {
-                const u64 src = rr < 0 ? top : (rr < P ? A[rr < 0 ? 0 : (rr < P ? rr : 0)] : bot);
-                const float lo = lo_of(src), hi = hi_of(src);
-                const float l = __shfl_up_sync(0xffffffffu, hi, 1), rt = __shfl_down_sync(0xffffffffu, lo, 1);
+            for (int rr = 0; rr < P; ++rr) {
+                const float lo = lo_of(A[rr]), hi = hi_of(A[rr]);
+                if (rr + 2 < P) {
+                    l[rr + 2] = __shfl_up_sync(0xffffffffu, hi_of(A[rr + 2]), 1);
+                    rt[rr + 2] = __shfl_down_sync(0xffffffffu, lo_of(A[rr + 2]), 1);
+                }
                 if (rr + 1 < P) {
                     const int i = rr + 1;
                     const u64 ci = ctile[i * 32];
-                    float x0 = lo_of(ci), x1 = hi_of(ci);
-                    x0 = fmaf(lo_of(nw[i][0]), l, x0);   x1 = fmaf(hi_of(nw[i][0]), lo, x1);
-                    x0 = fmaf(lo_of(nw[i][1]), lo, x0);  x1 = fmaf(hi_of(nw[i][1]), hi, x1);
-                    a0[i] = fmaf(lo_of(nw[i][2]), hi, x0); a1[i] = fmaf(hi_of(nw[i][2]), rt, x1);
+                    a0[i] = fmaf(lo_of(nw[i][1]), lo, lo_of(ci));  a1[i] = fmaf(hi_of(nw[i][0]), lo, hi_of(ci));
+                    a0[i] = fmaf(lo_of(nw[i][2]), hi, a0[i]);      a1[i] = fmaf(hi_of(nw[i][1]), hi, a1[i]);
+                    a0[i] = fmaf(lo_of(nw[i][0]), l[rr], a0[i]);   a1[i] = fmaf(hi_of(nw[i][2]), rt[rr], a1[i]);
                 }
-                if (rr >= 0 && rr < P) {
-                    const int i = rr < 0 ? 0 : (rr < P ? rr : 0);
-                    a0[i] = fmaf(lo_of(nw[i][4]), hi, fmaf(lo_of(nw[i][3]), l, a0[i]));
-                    a1[i] = fmaf(hi_of(nw[i][4]), rt, fmaf(hi_of(nw[i][3]), lo, a1[i]));
+                {
+                    const int i = rr;
+                    a0[i] = fmaf(lo_of(nw[i][4]), hi, a0[i]);      a1[i] = fmaf(hi_of(nw[i][3]), lo, a1[i]);
+                    a0[i] = fmaf(lo_of(nw[i][3]), l[rr], a0[i]);   a1[i] = fmaf(hi_of(nw[i][4]), rt[rr], a1[i]);
                 }
                 if (rr >= 1) {
                     const int i = rr - 1;
-                    float x0 = a0[i], x1 = a1[i];
-                    x0 = fmaf(lo_of(nw[i][5]), l, x0);   x1 = fmaf(hi_of(nw[i][5]), lo, x1);
-                    x0 = fmaf(lo_of(nw[i][6]), lo, x0);  x1 = fmaf(hi_of(nw[i][6]), hi, x1);
-                    x0 = fmaf(lo_of(nw[i][7]), hi, x0);  x1 = fmaf(hi_of(nw[i][7]), rt, x1);
-                    A[i] = pk(x0, x1);
+                    a0[i] = fmaf(lo_of(nw[i][6]), lo, a0[i]);      a1[i] = fmaf(hi_of(nw[i][5]), lo, a1[i]);
+                    a0[i] = fmaf(lo_of(nw[i][7]), hi, a0[i]);      a1[i] = fmaf(hi_of(nw[i][6]), hi, a1[i]);
+                    a0[i] = fmaf(lo_of(nw[i][5]), l[rr], a0[i]);   a1[i] = fmaf(hi_of(nw[i][7]), rt[rr], a1[i]);
+                    if (i >= 1) A[i] = pk(a0[i], a1[i]);          // complete, and the old row i is dead
                 }
             }
+            // rows -1 and P of the strip (zero above / below the CTA tile)
+            mbar_wait(smem_u32(&sm.row_bar[s][par]), (phases >> par) & 1u);
+            phases ^= 1u << par;
+            u64 top = 0ull, bot = 0ull;
+            if (wl > 0) top = *reinterpret_cast<const u64*>(&sm.rowbuf[s][par][wl - 1][1][2 * lane]);
+            if (wl < kSW - 1) bot = *reinterpret_cast<const u64*>(&sm.rowbuf[s][par][wl + 1][0][2 * lane]);
+            {
+                const float tlo = lo_of(top), thi = hi_of(top), blo = lo_of(bot), bhi = hi_of(bot);
+                const float tl = __shfl_up_sync(0xffffffffu, thi, 1), tr = __shfl_down_sync(0xffffffffu, tlo, 1);
+                const float bl = __shfl_up_sync(0xffffffffu, bhi, 1), br = __shfl_down_sync(0xffffffffu, blo, 1);
+                a1[0] = fmaf(hi_of(nw[0][0]), tlo, a1[0]);
+                a0[0] = fmaf(lo_of(nw[0][1]), tlo, a0[0]);  a1[0] = fmaf(hi_of(nw[0][1]), thi, a1[0]);
+                a0[0] = fmaf(lo_of(nw[0][2]), thi, a0[0]);
+                a1[P - 1] = fmaf(hi_of(nw[P - 1][5]), blo, a1[P - 1]);
+                a0[P - 1] = fmaf(lo_of(nw[P - 1][6]), blo, a0[P - 1]);  a1[P - 1] = fmaf(hi_of(nw[P - 1][6]), bhi, a1[P - 1]);
+                a0[P - 1] = fmaf(lo_of(nw[P - 1][7]), bhi, a0[P - 1]);
+                a0[0] = fmaf(lo_of(nw[0][0]), tl, a0[0]);  a1[0] = fmaf(hi_of(nw[0][2]), tr, a1[0]);
+                a0[P - 1] = fmaf(lo_of(nw[P - 1][5]), bl, a0[P - 1]);  a1[P - 1] = fmaf(hi_of(nw[P - 1][7]), br, a1[P - 1]);
+            }
+            A[0] = pk(a0[0], a1[0]);
+            A[P - 1] = pk(a0[P - 1], a1[P - 1]);
         };
 
-        // Ship the rim of slot s for refresh epoch e1: straight from the registers, data + tag in one 16-byte store.
-        auto ship = [&](int s, const u64 (&A)[P], int e1) {
-            const uint32_t tag = round_tag + (uint32_t)e1;
-            uint4* const base = out_base + (size_t)s * IB::size;
-            if (col_dst != kNone) {
-                uint4* d = base + col_dst + (e1 & 1) * IB::col_par;
-#pragma unroll
-                for (int i = 0; i < P; ++i) st_ll(d + i, A[i], tag);
-            }
-            if (rows_top || rows_bot) {                                          // warp-uniform
-                const u64 v0 = warp == 0 ? A[kHaloY] : A[P - 2 * kHaloY], v1 = warp == 0 ? A[kHaloY + 1] : A[P - 2 * kHaloY + 1];
-                if (row_dst != kNone) {
-                    uint4* d = base + row_dst + (e1 & 1) * IB::row_par;
-                    st_ll(d, v0, tag); st_ll(d + 32, v1, tag);
-                }
-                if (diag_dst != kNone) {
-                    uint4* d = base + diag_dst + (e1 & 1) * IB::row_par;
-                    st_ll(d, v0, tag); st_ll(d + 32, v1, tag);
-                }
-            }
-        };
-
-        // Start fetching the halo of slot s, refresh epoch e, from this CTA's inbox into the landing zone.
-        auto prefetch = [&](int s, int e) {
-            const uint4* box = my_box + (size_t)s * IB::size;
-            if (pf_col) cp_async16(smem_u32(&sm.colz[s][pf_sd][pf_row]), box + (e & 1) * IB::col_par + pf_sd * IB::col_side + pf_row);
-            if (rows_top || rows_bot) {
-                const int side = rows_bot ? 1 : 0;
-                const uint4* src = box + IB::row_base + (e & 1) * IB::row_par + side * IB::row_side + lane;
-#pragma unroll
-                for (int h = 0; h < kHaloY; ++h) cp_async16(smem_u32(&sm.rowz[s][side][h][lane]), src + h * 32);
-            }
-        };
-
-        // Take the halo ring of refresh epoch e.  Normal case: the prefetch issued half a period ago has landed with
-        // current tags.  Otherwise fetch again until the neighbours have delivered (bounded: fail loudly, never hang).
-        auto apply = [&](int s, u64 (&A)[P], int e, bool prefetched) {
-            const uint32_t tag = round_tag + (uint32_t)e;
-            if (!prefetched) prefetch(s, e);
-            for (int spin = 0;; ++spin) {
-                cp_async_wait_all();
-                __syncwarp();
-                bool ok = true;
-                if (edge) {
-#pragma unroll
-                    for (int i = 0; i < P; ++i) {
-                        const uint4 q = sm.colz[s][edge_sd][warp * P + i];
-                        ok = ok && q.y == tag && q.w == tag;
-                        A[i] = pk_bits(q.x, q.z);
-                    }
-                }
-                if (rows_top) {                                                   // after the columns: the corner comes with the rows
-#pragma unroll
-                    for (int h = 0; h < kHaloY; ++h) {
-                        const uint4 q = sm.rowz[s][0][h][lane];
-                        ok = ok && q.y == tag && q.w == tag;
-                        A[h] = pk_bits(q.x, q.z);
-                    }
-                }
-                if (rows_bot) {
-#pragma unroll
-                    for (int h = 0; h < kHaloY; ++h) {
-                        const uint4 q = sm.rowz[s][1][h][lane];
-                        ok = ok && q.y == tag && q.w == tag;
-                        A[P - kHaloY + h] = pk_bits(q.x, q.z);
-                    }
-                }
-                if (__all_sync(0xffffffffu, ok)) break;
-                if (spin > kSpinLimit || poisoned) { poisoned = true; break; }
-                __syncwarp();                                                     // everybody has read the landing zone
-                prefetch(s, e);
-            }
-        };
-
-        // ---- T steps, two at a time per slot ----------------------------------------------------------------------
+        DTRACE(5);
+        // ---- T steps; the halo ring is two pixels deep, so it is refreshed before every even step t >= 2 with the rim the
+        // neighbours staged after their previous odd step.  While this slot waits for its ring the other slot's warps have
+        // the issue slots to themselves. ----
         const int T_ = p.iters;
-        bool pfA = false, pfB = false;                      // a prefetch for the slot's next refresh is in flight
         for (int t = 0; t < T_; t += 2) {
             const int e = t >> 1;
-            const bool odd = t + 1 < T_, more = t + 2 < T_;
-            u64 top, bot;
-            // ===== slot A =====
-            if (multi && e > 0) { apply(0, A0, e, pfA); pfA = false; }
-            exchange_rows(0, 0, A0, top, bot);
-            sweep(nwA, A0, ctA, top, bot);
-            if (odd) {
-                exchange_rows(0, 1, A0, top, bot);
-                if (multi && haveB && e > 0) { prefetch(1, e); pfB = true; }      // B's rim messages left its neighbours a period ago
-                sweep(nwA, A0, ctA, top, bot);
-                if (multi && more) ship(0, A0, e + 1);
-            }
-            // ===== slot B =====
-            if (haveB) {
-                if (multi && e > 0) { apply(1, A1, e, pfB); pfB = false; }
-                exchange_rows(1, 0, A1, top, bot);
-                sweep(nwB, A1, ctB, top, bot);
-                if (odd) {
-                    exchange_rows(1, 1, A1, top, bot);
-                    if (multi && more) { prefetch(0, e + 1); pfA = true; }
-                    sweep(nwB, A1, ctB, top, bot);
-                    if (multi && more) ship(1, A1, e + 1);
+            if (multi && e > 0) {
+                // take the halo ring the communication warps have landed: columns first, then the rows (their lanes 0 / 31
+                // carry the corners, which come from the diagonal neighbours)
+                mbar_wait(smem_u32(&sm.halo_bar[s]), (phases >> 2) & 1u);
+                phases ^= 4u;
+                if (edge) {
+#pragma unroll
+                    for (int i = 0; i < P; ++i) A[i] = sm.land[s][edge_off + i];
+                }
+                if (rim_t) {
+#pragma unroll
+                    for (int h = 0; h < kHaloY; ++h) A[h] = sm.land[s][2 * TH + h * 32 + lane];
+                }
+                if (rim_b) {
+#pragma unroll
+                    for (int h = 0; h < kHaloY; ++h) A[P - kHaloY + h] = sm.land[s][2 * TH + 64 + h * 32 + lane];
                 }
             }
+            if (e < 24) DTRACE(8 + 4 * e);
+            step(0);
+            if (e < 24) DTRACE(9 + 4 * e);
+            if (t + 1 < T_) {
+                step(1);
+                if (e < 24) DTRACE(10 + 4 * e);
+                if (multi && t + 2 < T_) {
+                    // hand the rim (final now) to the slot's communication warps
+                    if (rim_l) {
+#pragma unroll
+                        for (int i = 0; i < P; ++i) sm.stage[s][wl * P + i] = A[i];
+                    }
+                    if (rim_r) {
+#pragma unroll
+                        for (int i = 0; i < P; ++i) sm.stage[s][TH + wl * P + i] = A[i];
+                    }
+                    if (rim_t) {
+#pragma unroll
+                        for (int h = 0; h < kHaloY; ++h) sm.stage[s][2 * TH + h * 32 + lane] = A[kHaloY + h];
+                    }
+                    if (rim_b) {
+#pragma unroll
+                        for (int h = 0; h < kHaloY; ++h) sm.stage[s][2 * TH + 64 + h * 32 + lane] = A[P - 2 * kHaloY + h];
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&sm.rim_bar[s]));
+                }
+            }
+            if (e < 24) DTRACE(11 + 4 * e);
         }
+        DTRACE(6);
 
         // ---- epilogue: only the final depth goes back to HBM, from the pixels this tile is authoritative for ----------
-        auto store_out = [&](const Geo& g, u64 (&A)[P]) {
+        {
+            const bool poisoned = *reinterpret_cast<volatile int*>(&sm.poison) != 0;
             // region of this unit whose results are exact (outside the decaying margin of unit edges inside the image)
-            const int vx0 = g.tix > 0 ? g.tix * p.stepx + p.margin : 0;
-            const int vx1 = g.tix == p.ntx - 1 ? W : g.tix * p.stepx + p.ew - p.margin;
-            const int vy0 = g.tiy > 0 ? g.tiy * p.stepy + p.margin : 0;
-            const int vy1 = g.tiy == p.nty - 1 ? H : g.tiy * p.stepy + p.eh - p.margin;
+            const int vx0 = tix > 0 ? tix * p.stepx + p.margin : 0;
+            const int vx1 = tix == p.ntx - 1 ? W : tix * p.stepx + p.ew - p.margin;
+            const int vy0 = tiy > 0 ? tiy * p.stepy + p.margin : 0;
+            const int vy1 = tiy == p.nty - 1 ? H : tiy * p.stepy + p.eh - p.margin;
             const int ry0 = hasU ? kHaloY : 0, ry1 = hasD ? TH - 1 - kHaloY : TH - 1;
-            const int gx = g.ox + 2 * lane;
-            T* ob = p.out + (size_t)g.plane * hw;
+            const int gx = ox + 2 * lane;
+            T* ob = p.out + (size_t)plane * hw;
             if (poisoned) {
 #pragma unroll
                 for (int i = 0; i < P; ++i) A[i] = pk(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000));
@@ -465,7 +543,7 @@ dual3x3_kernel(const __grid_constant__ DualParams<T> p, const __grid_constant__ 
                 const bool ok0 = gx >= vx0 && gx < vx1 && gx < W, ok1 = gx + 1 >= vx0 && gx + 1 < vx1 && gx + 1 < W;
 #pragma unroll
                 for (int i = 0; i < P; ++i) {
-                    const int ty = warp * P + i, gy = g.oy + ty;
+                    const int ty = wl * P + i, gy = oy + ty;
                     if (ty < ry0 || ty > ry1 || gy < vy0 || gy >= vy1 || gy >= H) continue;
                     const size_t off = (size_t)gy * W + gx;
                     if (ok0 && ok1) {
@@ -477,19 +555,9 @@ dual3x3_kernel(const __grid_constant__ DualParams<T> p, const __grid_constant__ 
                     }
                 }
             }
-        };
-        store_out(geo_of(unit_a), A0);
-        if (haveB) store_out(geo_of(unit_b), A1);
-
-        if (multi) {
-            // Every message addressed to this CTA in this round has been consumed (the last refresh is followed by at
-            // least one CTA barrier): leave the inboxes clean for the round after next / the next launch / graph replay.
-            const uint32_t nclean = (haveB ? 2u : 1u) * IB::size;
-            for (uint32_t i = threadIdx.x; i < nclean; i += NW * 32) my_box[i] = make_uint4(0, 0, 0, 0);
-            __threadfence();
         }
+        DTRACE(7);
     }
-    if (poisoned && p.status) *p.status = 1;
 }
 
 // ---- host side -------------------------------------------------------------------------------------------------------
@@ -502,7 +570,7 @@ struct DualPlan {
 
 inline int dual_force_p()
 {
-    static const int v = [] { const char* e = getenv("CSPN_DUAL_P"); return e ? atoi(e) : 0; }();   // tuning knob: 4 or 5
+    static const int v = [] { const char* e = getenv("CSPN_DUAL_P"); return e ? atoi(e) : 0; }();   // tuning knob: 8 or 10
     return v;
 }
 
@@ -513,9 +581,9 @@ DualPlan dual_plan(int H, int W, int iters, long planes, int sms)
 {
     DualPlan best{}; best.ok = false;
     if (planes < 1 || iters < 1 || iters > 120 || (W & 1)) return best;
-    for (int P = 4; P <= 5; ++P) {
+    for (int P = 8; P <= 10; P += 2) {
         if (dual_force_p() && dual_force_p() != P) continue;
-        const int th = kDNW * P, step_y = th - 2 * kHaloY;
+        const int th = kSW * P, step_y = th - 2 * kHaloY;
         const int cx_full = W <= kTileW ? 1 : (W - kTileW + kStepX - 1) / kStepX + 1;
         const int cy_full = H <= th ? 1 : (H - th + step_y - 1) / step_y + 1;
         for (int cx = 1; cx <= cx_full; ++cx)
@@ -538,7 +606,7 @@ DualPlan dual_plan(int H, int W, int iters, long planes, int sms)
                 d.rounds = (int)rounds;
                 const long n0 = d.units < upr ? d.units : upr;
                 d.grid = (int)((n0 + 1) / 2) * d.per_unit;
-                const double hs = 56.0 * P;
+                const double hs = 28.0 * P;
                 const double period = d.units >= 2 ? 4 * hs + 600 : 2 * hs + 1100;
                 d.cost = (double)rounds * (11000.0 + ((iters + 1) / 2) * period);
                 d.ok = true;
@@ -548,19 +616,19 @@ DualPlan dual_plan(int H, int W, int iters, long planes, int sms)
     return best;
 }
 
-template <int P> constexpr size_t dual_inbox_bytes(int grid) { return (size_t)2 * grid * 2 * InboxGeom<kDNW * P>::size * sizeof(uint4); }
+template <int P> constexpr size_t dual_inbox_bytes(int grid) { return (size_t)2 * grid * 2 * Msg<P>::inbox * sizeof(uint4); }
 constexpr size_t kDualStatusBytes = 256;
 
 inline size_t dual_ws_bytes(const DualPlan& d)
 {
     if (d.per_unit <= 1) return kDualStatusBytes;
-    return kDualStatusBytes + (d.P == 4 ? dual_inbox_bytes<4>(d.grid) : dual_inbox_bytes<5>(d.grid));
+    return kDualStatusBytes + (d.P == 8 ? dual_inbox_bytes<8>(d.grid) : dual_inbox_bytes<10>(d.grid));
 }
 
 template <typename T, int P, int MODE>
 int dual_launch(const FwdArgs<T>& a, const DualPlan& d, const CUtensorMap& map)
 {
-    constexpr int TH = kDNW * P;
+    constexpr int TH = kSW * P;
     using St = Stage<T, TH, MODE>;
     constexpr size_t smem = ((sizeof(DualSm<P>) + 127) & ~(size_t)127) + 2 * St::bytes;
     static_assert(smem <= 227 * 1024, "shared memory budget of one SM exceeded");
@@ -586,7 +654,7 @@ int dual_launch(const FwdArgs<T>& a, const DualPlan& d, const CUtensorMap& map)
     p.tag_base = exchange_epoch().fetch_add(1, std::memory_order_relaxed) << 20;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)d.grid);
-    cfg.blockDim = dim3(kDNW * 32);
+    cfg.blockDim = dim3(kDThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = a.stream;
     cudaLaunchAttribute at[1];
@@ -615,6 +683,14 @@ int device_sms()
 DualPlan plan_for(int B, int C, int H, int W, int iters) { return dual_plan(H, W, iters, (long)B * C, device_sms()); }
 
 }  // namespace
+
+#ifdef CSPN_TRACE
+extern "C" __attribute__((visibility("default"))) int cspn_debug_set_trace_dual(void* buf)
+{
+    long long* ptr = (long long*)buf;
+    return (int)cudaMemcpyToSymbol(g_dtrace, &ptr, sizeof ptr);
+}
+#endif
 
 bool dual_supported(int B, int C, int H, int W, int iters, int ksize, int mode)
 {
@@ -651,11 +727,11 @@ int dual_forward(const FwdArgs<T>& a)
     alignas(64) CUtensorMap map;
     memset(&map, 0, sizeof map);
     bool tma;
-    if (a.mode == CSPN_MODE_NEW) tma = d.P == 4 ? make_guidance_map<T, 32, CSPN_MODE_NEW>(a.guidance, a.gbs, a.B, a.H, a.W, &map) : make_guidance_map<T, 40, CSPN_MODE_NEW>(a.guidance, a.gbs, a.B, a.H, a.W, &map);
-    else tma = d.P == 4 ? make_guidance_map<T, 32, CSPN_MODE_OURS>(a.guidance, a.gbs, a.B, a.H, a.W, &map) : make_guidance_map<T, 40, CSPN_MODE_OURS>(a.guidance, a.gbs, a.B, a.H, a.W, &map);
+    if (a.mode == CSPN_MODE_NEW) tma = d.P == 8 ? make_guidance_map<T, 32, CSPN_MODE_NEW>(a.guidance, a.gbs, a.B, a.H, a.W, &map) : make_guidance_map<T, 40, CSPN_MODE_NEW>(a.guidance, a.gbs, a.B, a.H, a.W, &map);
+    else tma = d.P == 8 ? make_guidance_map<T, 32, CSPN_MODE_OURS>(a.guidance, a.gbs, a.B, a.H, a.W, &map) : make_guidance_map<T, 40, CSPN_MODE_OURS>(a.guidance, a.gbs, a.B, a.H, a.W, &map);
     if (!tma) return kDualFallback;
-    if (a.mode == CSPN_MODE_NEW) return d.P == 4 ? dual_launch<T, 4, CSPN_MODE_NEW>(a, d, map) : dual_launch<T, 5, CSPN_MODE_NEW>(a, d, map);
-    return d.P == 4 ? dual_launch<T, 4, CSPN_MODE_OURS>(a, d, map) : dual_launch<T, 5, CSPN_MODE_OURS>(a, d, map);
+    if (a.mode == CSPN_MODE_NEW) return d.P == 8 ? dual_launch<T, 8, CSPN_MODE_NEW>(a, d, map) : dual_launch<T, 10, CSPN_MODE_NEW>(a, d, map);
+    return d.P == 8 ? dual_launch<T, 8, CSPN_MODE_OURS>(a, d, map) : dual_launch<T, 10, CSPN_MODE_OURS>(a, d, map);
 }
 
 template int dual_forward<float>(const FwdArgs<float>&);

@@ -72,6 +72,10 @@ extern "C" {
 #define CSPN_ERR_WORKSPACE (-6)      /* workspace NULL or too small */
 #define CSPN_ERR_BAD_SPARSE_CHANNELS (-7)
 #define CSPN_ERR_ALIAS (-8)          /* out aliases an input */
+#define CSPN_ERR_EXCHANGE_TIMEOUT (-9) /* host entry points only: a tile of a fused kernel never received its neighbours' halo ring
+                                          (bounded spin expired; the output is NaN-filled).  Device entry points are asynchronous:
+                                          a CSPN_KERNEL_DUAL forward (cspn_fwd_plan) reports it through the first int of
+                                          `workspace` (0 = fine, 1 = timeout), valid once the stream has reached the end of the call. */
 
 /* path selection (cspn_set_path): which CUDA implementation the forward uses */
 #define CSPN_PATH_AUTO 0    /* fused single-launch kernel whenever the configuration is supported */
@@ -134,6 +138,21 @@ CSPN_API int cspn_fwd_host_f32(const float* guidance, int64_t guidance_batch_str
 CSPN_API int cspn_fwd_host_f16(const void* guidance, int64_t guidance_batch_stride,
                       const void* depth, const void* sparse, int sparse_channels, void* out,
                       int B, int C, int H, int W, int iters, int ksize, int mode, void* stream);
+
+/* Pipelined host-buffer forward: cspn_fwd_host_submit_* enqueues H2D copy -> kernels -> D2H copy on a library-owned
+ * stream and returns at once with a ticket (> 0; 0 for an empty batch); cspn_host_wait(ticket) blocks until `out` of
+ * that call is valid and returns its status.  Up to cspn_host_pipeline_depth() calls of a host thread are in flight per
+ * device: the H2D copy of one call overlaps the kernel and the D2H copy of the previous one.  A further submit first waits
+ * for the oldest call in flight.  The host buffers (ideally pinned) must stay valid and unmodified until the call has been
+ * waited for.  Tickets belong to the submitting host thread and device. */
+CSPN_API int cspn_fwd_host_submit_f32(const float* guidance, int64_t guidance_batch_stride,
+                      const float* depth, const float* sparse, int sparse_channels, float* out,
+                      int B, int C, int H, int W, int iters, int ksize, int mode, int* ticket);
+CSPN_API int cspn_fwd_host_submit_f16(const void* guidance, int64_t guidance_batch_stride,
+                      const void* depth, const void* sparse, int sparse_channels, void* out,
+                      int B, int C, int H, int W, int iters, int ksize, int mode, int* ticket);
+CSPN_API int cspn_host_wait(int ticket);
+CSPN_API int cspn_host_pipeline_depth(void);
 
 #ifdef __cplusplus
 }

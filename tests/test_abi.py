@@ -86,15 +86,15 @@ def test_planner_picks_kernel_and_workspace_by_problem_size():
     lib = _lib.load()
 
     def dual_ws(ctas, p):
-        return 256 + 2 * ctas * 2 * (4 * 8 * p + 4 * 2 * 32) * 16
+        return 256 + 2 * ctas * 2 * 2 * (2 * 4 * p + 4 * 32) * 16        # two parities of (2 TH + 128) messages, TH = 4 p
 
-    plan = _lib.forward_plan(8, 1, 228, 304, 24)                      # headline: 8 images x 35 tiles of 64x40, one round
-    assert plan == dict(kernel=_lib.KERNEL_DUAL, rows_per_warp=5, cx=5, cy=7, ntx=1, nty=1, ctas=140, rounds=1, units_per_class=4, units=8)
-    assert lib.cspn_fwd_workspace_bytes(8, 1, 228, 304, 24, 3, 0) >= dual_ws(140, 5)
+    plan = _lib.forward_plan(8, 1, 228, 304, 24)                      # headline: 8 images x 35 tiles of 64x40 (4 warps x 10 rows), one round
+    assert plan == dict(kernel=_lib.KERNEL_DUAL, rows_per_warp=10, cx=5, cy=7, ntx=1, nty=1, ctas=140, rounds=1, units_per_class=4, units=8)
+    assert lib.cspn_fwd_workspace_bytes(8, 1, 228, 304, 24, 3, 0) >= dual_ws(140, 10)
     plan = _lib.forward_plan(32, 1, 352, 1216, 24)                    # KITTI: half images of 21x7 tiles of 64x32, a round per image
-    assert (plan["kernel"], plan["rows_per_warp"], plan["ntx"] * plan["nty"], plan["rounds"]) == (_lib.KERNEL_DUAL, 4, 2, 32)
+    assert (plan["kernel"], plan["rows_per_warp"], plan["ntx"] * plan["nty"], plan["rounds"]) == (_lib.KERNEL_DUAL, 8, 2, 32)
     assert 140 <= plan["cx"] * plan["cy"] == plan["ctas"] <= 148
-    assert lib.cspn_fwd_workspace_bytes(32, 1, 352, 1216, 24, 3, 0) >= dual_ws(plan["ctas"], 4)
+    assert lib.cspn_fwd_workspace_bytes(32, 1, 352, 1216, 24, 3, 0) >= dual_ws(plan["ctas"], 8)
     plan = _lib.forward_plan(1, 1, 1080, 1440, 24)                    # one image larger than the GPU: resident units with margins
     assert plan["kernel"] == _lib.KERNEL_DUAL and plan["cx"] * plan["cy"] <= 148 and plan["ntx"] * plan["nty"] > 1
     assert _lib.forward_plan(3, 1, 97, 131, 24)["kernel"] == _lib.KERNEL_SINGLE          # odd width: plain-load prologue kernel
