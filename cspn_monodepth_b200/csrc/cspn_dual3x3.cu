@@ -31,15 +31,17 @@ namespace {
 __device__ long long* g_dtrace = nullptr;
 constexpr int kDTraceSlots = 128;
 #define DTRACE(slot) do { if (g_dtrace && (threadIdx.x & 31) == 0) g_dtrace[((size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kDTraceSlots + (slot)] = clock64(); } while (0)
+// per-refresh stamps: SM clock in slot 8 + 4 e + k, global nanosecond timer in slot 64 + 4 e + k (e < 12, k < 4)
+#define DTRACE_E(e, k) do { if (g_dtrace && (threadIdx.x & 31) == 0 && (e) < 12) { long long* t_ = g_dtrace + ((size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kDTraceSlots; \
+    unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); t_[8 + 4 * (e) + (k)] = clock64(); t_[64 + 4 * (e) + (k)] = (long long)gt_; } } while (0)
 #else
 #define DTRACE(slot) do { } while (0)
+#define DTRACE_E(e, k) do { } while (0)
 #endif
 
 constexpr int kSW = 4;                       // compute warps per slot: the slot's tile is 64 x (4 * P) pixels
 constexpr int kDNW = 2 * kSW;                // compute warps per CTA: warps 0-3 = slot A, 4-7 = slot B
-constexpr int kCommWarps = 4;                // one warp group: warps 8, 10 serve slot A, warps 9, 11 slot B
-constexpr int kDThreads = (kDNW + kCommWarps) * 32;
-constexpr int kRegsCompute = 232, kRegsComm = 40;      // setmaxnreg: 256 x 232 + 128 x 40 = 384 x 168 registers
+constexpr int kDThreads = kDNW * 32;
 constexpr uint32_t kNone = 0xffffffffu;
 constexpr int kSpinLimit = 1 << 20;
 
@@ -80,13 +82,9 @@ template <int P> struct Msg {
 template <int P>
 struct __align__(128) DualSm {
     float rowbuf[2][2][kSW][2][kTileW];      // [slot][step parity][warp][first / last row of the warp's strip][x]
-    u64 stage[2][Msg<P>::n];                 // outgoing rim of slot s (compute warps -> communication warps)
-    u64 land[2][Msg<P>::n];                  // incoming halo ring of slot s (communication warps -> compute warps)
+    u64 colbox[2][kSW][2][16];               // [slot][warp][side][row of the warp's strip]: halo columns on their way from the polling lanes to the edge lanes
     u64 tma_bar[2][8];
     u64 row_bar[2][2];                       // [slot][step parity]: the slot's 4 compute warps have published their edge rows
-    u64 rim_bar[2];                          // slot s: the rim is staged (4 arrivals, one per compute warp)
-    u64 halo_bar[2];                         // slot s: the halo ring has landed (2 arrivals, one per communication warp)
-    int poison;
 };
 
 __device__ __forceinline__ u64 pk_bits(uint32_t lo, uint32_t hi)
@@ -104,115 +102,13 @@ __device__ __forceinline__ void slot_bar_sync(int s)      // the 4 compute warps
     asm volatile("bar.sync %0, %1;" :: "r"(1 + s), "n"(kSW * 32) : "memory");
 }
 
-// ---- communication warp `half` (0 / 1) of slot s: ships the staged rim to the neighbours' inboxes and polls this tile's
-// inbox; the two warps of a slot split the 32-message groups (even / odd) ----------------------------------------------
-template <typename T, int P>
-__device__ __forceinline__ void comm_role(const DualParams<T>& p, DualSm<P>& sm, const int s, const int half, const int lane)
-{
-    using M = Msg<P>;
-    constexpr int TH = M::TH;
-    const int w = blockIdx.x;
-    const int uidx = w / p.per_unit, within = w - uidx * p.per_unit;
-    const int ccy = within / p.cx, ccx = within - ccy * p.cx;
-    const bool hasL = ccx > 0, hasR = ccx < p.cx - 1, hasU = ccy > 0, hasD = ccy < p.cy - 1;
-    if (p.per_unit <= 1) return;                              // single-tile units exchange nothing
-    const int E = (p.iters + 1) / 2 - 1;                      // refreshes per round
-    if (E <= 0) return;
-
-    // per-lane message tables (refresh parity 0, round parity 0): where staged message k * 32 + lane goes, and whether
-    // inbox entry k * 32 + lane is expected
-    uint32_t dst[M::KH];
-    uint32_t need = 0u;
-#pragma unroll
-    for (int j = 0; j < M::KH; ++j) {
-        const int k = 2 * j + half;
-        const int idx = k * 32 + lane;
-        dst[j] = kNone;
-        int nb = -1, in_idx = 0;
-        if (k >= M::K) continue;
-        if (idx < TH) { if (hasL) { nb = w - 1; in_idx = TH + idx; need |= 1u << j; } }
-        else if (idx < 2 * TH) { if (hasR) { nb = w + 1; in_idx = idx - TH; need |= 1u << j; } }
-        else if (idx < M::n) {
-            const int q = idx - 2 * TH, bottom = q >> 6, l = q & 31;
-            const bool own = !(l == 0 && hasL) && !(l == 31 && hasR);
-            if (!bottom) { if (hasU) { need |= 1u << j; if (own) { nb = w - p.cx; in_idx = 2 * TH + 64 + (q & 63); } } }
-            else { if (hasD) { need |= 1u << j; if (own) { nb = w + p.cx; in_idx = 2 * TH + (q & 63); } } }
-        }
-        if (nb >= 0) dst[j] = (uint32_t)(nb * 2 + s) * M::inbox + (uint32_t)in_idx;
-    }
-    // corners (warp `half` 1): lanes 0..7 = (top / bottom rim rows) x (left / right rim lane) x (row h) -> diagonal neighbour's corner lane
-    uint32_t cdst = kNone, csrc = 0u;
-    if (half == 1 && lane < 8) {
-        const bool bottom = lane & 4, right = lane & 2; const int h = lane & 1;
-        if ((bottom ? hasD : hasU) && (right ? hasR : hasL)) {
-            const int nb = w + (bottom ? p.cx : -p.cx) + (right ? 1 : -1);
-            csrc = (uint32_t)(2 * TH + (bottom ? 64 : 0) + h * 32 + (right ? 30 : 1));
-            cdst = (uint32_t)(nb * 2 + s) * M::inbox + (uint32_t)(2 * TH + (bottom ? 0 : 64) + h * 32 + (right ? 0 : 31));
-        }
-    }
-
-    uint32_t rim_phase = 0u;
-    bool poisoned = false;
-    for (int r = 0; r < p.rounds; ++r) {
-        const int first = r * 2 * p.nA;
-        const int n = min(p.total_units - first, 2 * p.nA);
-        const int nAr = (n + 1) >> 1;
-        if (uidx >= nAr) break;
-        if (s == 1 && uidx >= n - nAr) break;               // no slot B in this (last) round
-        uint4* const set_base = p.inbox + (size_t)(r & 1) * gridDim.x * 2u * M::inbox;
-        uint4* const my_box = set_base + (size_t)(w * 2 + s) * M::inbox;
-        const uint32_t round_tag = p.tag_base + ((uint32_t)r << 6);
-        for (int e1 = 1; e1 <= E; ++e1) {
-            const uint32_t tag = round_tag + (uint32_t)e1;
-            const uint32_t par_off = (uint32_t)(e1 & 1) * M::n;
-            // ---- ship: the compute warps have staged the rim of refresh e1 ----
-            mbar_wait(smem_u32(&sm.rim_bar[s]), rim_phase);
-            rim_phase ^= 1u;
-#pragma unroll
-            for (int j = 0; j < M::KH; ++j)
-                if (dst[j] != kNone) st_ll(set_base + dst[j] + par_off, sm.stage[s][(2 * j + half) * 32 + lane], tag);
-            if (cdst != kNone) st_ll(set_base + cdst + par_off, sm.stage[s][csrc], tag);
-            // ---- poll: the neighbours' rims of the same refresh (they ship at about the same time: the first look would
-            // always come too early, so it is delayed by roughly one store latency) ----
-            const uint4* box = my_box + par_off + half * 32 + lane;
-            uint4 q[M::KH];
-#pragma unroll
-            for (int j = 0; j < M::KH; ++j)
-                if (need >> j & 1u) q[j] = ld_ll(box + j * 64);
-            for (int spin = 0;; ++spin) {
-                bool ok = true;
-#pragma unroll
-                for (int j = 0; j < M::KH; ++j)
-                    if ((need >> j & 1u) && !(q[j].y == tag && q[j].w == tag)) { ok = false; q[j] = ld_ll(box + j * 64); }
-                if (__all_sync(0xffffffffu, ok)) break;
-                if (spin > kSpinLimit || poisoned) { poisoned = true; break; }      // neighbours never showed up: fail loudly, do not hang
-            }
-#pragma unroll
-            for (int j = 0; j < M::KH; ++j)
-                if (need >> j & 1u) sm.land[s][(2 * j + half) * 32 + lane] = pk_bits(q[j].x, q[j].z);
-            if (poisoned) sm.poison = 1;
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&sm.halo_bar[s]));
-        }
-        // every message addressed to this tile in this round has been consumed: leave the inbox clean for the round after
-        // next / the next launch / graph replay
-        // (each warp cleans exactly the entries it polls: its partner may still be waiting for its own)
-#pragma unroll
-        for (int j = 0; j < M::KH; ++j) {
-            const int idx = (2 * j + half) * 32 + lane;
-            if (idx < M::n) { my_box[idx] = make_uint4(0, 0, 0, 0); my_box[M::n + idx] = make_uint4(0, 0, 0, 0); }
-        }
-        __threadfence();
-    }
-    if (poisoned && p.status && lane == 0) *p.status = 1;
-}
-
 template <typename T, int P, int MODE>
 __global__ void __launch_bounds__(kDThreads, 1)
 dual3x3_kernel(const __grid_constant__ DualParams<T> p, const __grid_constant__ CUtensorMap gmap)
 {
     constexpr int TH = kSW * P, STEPY = TH - 2 * kHaloY;
     static_assert(P >= 4, "rim rows 2,3 / P-4,P-3 must live in the first / last warp");
+    static_assert(P <= 16, "halo column polling: one lane per row of the warp's strip, left column in lanes 0-15, right in 16-31");
     using St = Stage<T, TH, MODE>;
     typedef typename std::conditional<sizeof(T) == 4, float2, __half2>::type V2;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -228,24 +124,13 @@ dual3x3_kernel(const __grid_constant__ DualParams<T> p, const __grid_constant__ 
             for (int k = 0; k < 8; ++k) mbar_init(smem_u32(&sm.tma_bar[s][k]), 1);
             mbar_init(smem_u32(&sm.row_bar[s][0]), kSW);
             mbar_init(smem_u32(&sm.row_bar[s][1]), kSW);
-            mbar_init(smem_u32(&sm.rim_bar[s]), kSW);
-            mbar_init(smem_u32(&sm.halo_bar[s]), 2);
         }
-        sm.poison = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if (blockIdx.x == 0 && p.status) *p.status = 0;      // a timeout (2^20 polls later at the earliest) sets it to 1
     }
     __syncthreads();
 
-    if (warp >= kDNW) {
-        // ===== communication warp group: hands its registers to the compute warps =====
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(kRegsComm));
-        comm_role<T, P>(p, sm, (warp - kDNW) & 1, (warp - kDNW) >> 1, lane);
-        return;
-    }
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(kRegsCompute));
-
-    // ===== compute warps: warp group s owns slot s =====
+    // ===== warp group s (4 warps) owns slot s =====
     const int s = warp / kSW, wl = warp - s * kSW;           // slot, warp within the slot's tile
     T* const stage = reinterpret_cast<T*>(smem_raw + kStageOff + (size_t)s * St::bytes);
     // The re-injection term c lives where the guidance was staged (read once per row and step; every thread only re-reads
@@ -265,9 +150,40 @@ dual3x3_kernel(const __grid_constant__ DualParams<T> p, const __grid_constant__ 
     const bool rim_l = multi && lane == 1 && hasL, rim_r = multi && lane == 30 && hasR;
     const bool rim_t = multi && wl == 0 && hasU, rim_b = multi && wl == kSW - 1 && hasD;       // warp-uniform
     const bool edge = multi && ((lane == 0 && hasL) || (lane == 31 && hasR));
-    const int edge_off = (lane == 31 ? TH : 0) + wl * P;
 
-    uint32_t phases = 0u;        // bit par: phase of row_bar[s][par]; bit 2: phase of halo_bar[s]
+    // Outgoing messages of this lane, as uint4 offsets from the inbox set of the round, refresh parity 0 (see Msg):
+    //   col_dst  lanes 1 / 30: my rim column, all P rows of the warp -> left neighbour's right / right neighbour's left halo column
+    //   row_dst  first / last warp: my rim rows 2,3 / TH-4,TH-3 -> upper neighbour's bottom / lower neighbour's top halo rows,
+    //            except the lanes whose pixels I do not own (lane 0 / 31 next to a left / right neighbour)
+    //   diag_dst first / last warp, lanes 1 / 30: the same rim rows -> the corner lane (31 / 0) of the DIAGONAL neighbour's rows
+    using M = Msg<P>;
+    uint32_t col_dst = kNone, row_dst = kNone, diag_dst = kNone;
+    if (multi) {
+        if (lane == 1 && hasL) col_dst = (uint32_t)((w - 1) * 2 + s) * M::inbox + (uint32_t)(TH + wl * P);
+        if (lane == 30 && hasR) col_dst = (uint32_t)((w + 1) * 2 + s) * M::inbox + (uint32_t)(wl * P);
+        const bool own = !(lane == 0 && hasL) && !(lane == 31 && hasR);
+        if (rim_t) {
+            const uint32_t up = (uint32_t)((w - p.cx) * 2 + s) * M::inbox + (uint32_t)(2 * TH + 64);
+            if (own) row_dst = up + (uint32_t)lane;
+            if (lane == 1 && hasL) diag_dst = up - 2u * M::inbox + 31u;
+            if (lane == 30 && hasR) diag_dst = up + 2u * M::inbox;
+        }
+        if (rim_b) {
+            const uint32_t dn = (uint32_t)((w + p.cx) * 2 + s) * M::inbox + (uint32_t)(2 * TH);
+            if (own) row_dst = dn + (uint32_t)lane;
+            if (lane == 1 && hasL) diag_dst = dn - 2u * M::inbox + 31u;
+            if (lane == 30 && hasR) diag_dst = dn + 2u * M::inbox;
+        }
+    }
+
+    // what this lane polls from the tile's own inbox: lanes 0..P-1 the left halo column of the warp's rows, lanes 16..16+P-1
+    // the right one (one entry each), the first / last warp in addition the two top / bottom halo rows (one entry per lane and row)
+    const int poll_sd = lane >> 4, poll_i = lane & 15;
+    const bool poll_col = multi && poll_i < P && (poll_sd == 0 ? hasL : hasR);
+    const uint32_t poll_col_idx = (uint32_t)(poll_sd * TH + wl * P + poll_i);
+    const uint32_t poll_row_idx = (uint32_t)(2 * TH + (rim_b ? 64 : 0) + lane);
+    uint32_t phases = 0u;        // bit par: phase of row_bar[s][par]
+    bool poisoned = false;
 
     for (int r = 0; r < p.rounds; ++r) {
         // ---- which unit this slot serves in round r ------------------------------------------------------------
@@ -277,6 +193,9 @@ dual3x3_kernel(const __grid_constant__ DualParams<T> p, const __grid_constant__ 
         if (uidx >= nAr) break;                             // later rounds are never larger
         if (s == 1 && uidx >= n - nAr) break;               // no slot B in this (last) round
         const int unit = first + (s ? nAr : 0) + uidx;
+        uint4* const set_base = p.inbox + (size_t)(r & 1) * gridDim.x * 2u * M::inbox;
+        uint4* const my_box = set_base + (size_t)(w * 2 + s) * M::inbox;
+        const uint32_t round_tag = p.tag_base + ((uint32_t)r << 6);
 
         const int upp = p.ntx * p.nty;
         const int plane = unit / upp, sub = unit - plane * upp;
@@ -475,58 +394,66 @@ dual3x3_kernel(const __grid_constant__ DualParams<T> p, const __grid_constant__ 
         for (int t = 0; t < T_; t += 2) {
             const int e = t >> 1;
             if (multi && e > 0) {
-                // take the halo ring the communication warps have landed: columns first, then the rows (their lanes 0 / 31
-                // carry the corners, which come from the diagonal neighbours)
-                mbar_wait(smem_u32(&sm.halo_bar[s]), (phases >> 2) & 1u);
-                phases ^= 4u;
-                if (edge) {
-#pragma unroll
-                    for (int i = 0; i < P; ++i) A[i] = sm.land[s][edge_off + i];
-                }
-                if (rim_t) {
-#pragma unroll
-                    for (int h = 0; h < kHaloY; ++h) A[h] = sm.land[s][2 * TH + h * 32 + lane];
-                }
-                if (rim_b) {
-#pragma unroll
-                    for (int h = 0; h < kHaloY; ++h) A[P - kHaloY + h] = sm.land[s][2 * TH + 64 + h * 32 + lane];
-                }
-            }
-            if (e < 24) DTRACE(8 + 4 * e);
-            step(0);
-            if (e < 24) DTRACE(9 + 4 * e);
-            if (t + 1 < T_) {
-                step(1);
-                if (e < 24) DTRACE(10 + 4 * e);
-                if (multi && t + 2 < T_) {
-                    // hand the rim (final now) to the slot's communication warps
-                    if (rim_l) {
-#pragma unroll
-                        for (int i = 0; i < P; ++i) sm.stage[s][wl * P + i] = A[i];
+                // Take the halo ring of refresh e: re-read this warp's inbox entries until every tag is current (data and tag
+                // travel in the same 16-byte store).  While this warp waits on L2, the other slot's warps have the SM.
+                const uint32_t tag = round_tag + (uint32_t)e;
+                const uint4* box = my_box + (uint32_t)(e & 1) * M::n;
+                const uint4 have = make_uint4(0, tag, 0, tag), want = make_uint4(0, ~tag, 0, ~tag);     // lanes / warps that poll nothing are satisfied from the start
+                uint4 qc = poll_col ? want : have, q0 = (rim_t || rim_b) ? want : have, q1 = q0;
+                const long long t0 = clock64();
+                for (;;) {
+                    if (poll_col && !(qc.y == tag && qc.w == tag)) qc = ld_ll(box + poll_col_idx);
+                    if (rim_t || rim_b) {
+                        if (!(q0.y == tag && q0.w == tag)) q0 = ld_ll(box + poll_row_idx);
+                        if (!(q1.y == tag && q1.w == tag)) q1 = ld_ll(box + poll_row_idx + 32);
                     }
-                    if (rim_r) {
+                    const bool ok = qc.y == tag && qc.w == tag && q0.y == tag && q0.w == tag && q1.y == tag && q1.w == tag;
+                    if (__all_sync(0xffffffffu, ok)) break;
+                    if (poisoned || clock64() - t0 > 4000000000ll) { poisoned = true; break; }     // neighbours never showed up: fail loudly (~2 s), do not hang
+                }
+                // columns first (through shared memory to the edge lanes), then the rows: their lanes 0 / 31 carry the corners,
+                // which come from the diagonal neighbours
+                if (hasL || hasR) {
+                    if (poll_col) sm.colbox[s][wl][poll_sd][poll_i] = pk_bits(qc.x, qc.z);
+                    __syncwarp();
+                    if (edge) {
 #pragma unroll
-                        for (int i = 0; i < P; ++i) sm.stage[s][TH + wl * P + i] = A[i];
-                    }
-                    if (rim_t) {
-#pragma unroll
-                        for (int h = 0; h < kHaloY; ++h) sm.stage[s][2 * TH + h * 32 + lane] = A[kHaloY + h];
-                    }
-                    if (rim_b) {
-#pragma unroll
-                        for (int h = 0; h < kHaloY; ++h) sm.stage[s][2 * TH + 64 + h * 32 + lane] = A[P - 2 * kHaloY + h];
+                        for (int i = 0; i < P; ++i) A[i] = sm.colbox[s][wl][lane == 31 ? 1 : 0][i];
                     }
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(&sm.rim_bar[s]));
+                }
+                if (rim_t) { A[0] = pk_bits(q0.x, q0.z); A[1] = pk_bits(q1.x, q1.z); }
+                if (rim_b) { A[P - 2] = pk_bits(q0.x, q0.z); A[P - 1] = pk_bits(q1.x, q1.z); }
+            }
+            DTRACE_E(e, 0);
+            step(0);
+            DTRACE_E(e, 1);
+            if (t + 1 < T_) {
+                step(1);
+                DTRACE_E(e, 2);
+                if (multi && t + 2 < T_) {
+                    // ship the rim (final now) of refresh e + 1 straight from the registers: data + tag in one 16-byte store
+                    const uint32_t tag = round_tag + (uint32_t)(e + 1);
+                    uint4* const base = set_base + (uint32_t)((e + 1) & 1) * M::n;
+                    if (col_dst != kNone) {
+                        uint4* d = base + col_dst;
+#pragma unroll
+                        for (int i = 0; i < P; ++i) st_ll(d + i, A[i], tag);
+                    }
+                    if (rim_t || rim_b) {                                          // warp-uniform
+                        const u64 v0 = rim_t ? A[kHaloY] : A[P - 2 * kHaloY], v1 = rim_t ? A[kHaloY + 1] : A[P - 2 * kHaloY + 1];
+                        if (row_dst != kNone) { st_ll(base + row_dst, v0, tag); st_ll(base + row_dst + 32, v1, tag); }
+                        if (diag_dst != kNone) { st_ll(base + diag_dst, v0, tag); st_ll(base + diag_dst + 32, v1, tag); }
+                    }
                 }
             }
-            if (e < 24) DTRACE(11 + 4 * e);
+            DTRACE_E(e, 3);
         }
         DTRACE(6);
 
         // ---- epilogue: only the final depth goes back to HBM, from the pixels this tile is authoritative for ----------
         {
-            const bool poisoned = *reinterpret_cast<volatile int*>(&sm.poison) != 0;
+            if (poisoned && p.status && lane == 0) *p.status = 1;
             // region of this unit whose results are exact (outside the decaying margin of unit edges inside the image)
             const int vx0 = tix > 0 ? tix * p.stepx + p.margin : 0;
             const int vx1 = tix == p.ntx - 1 ? W : tix * p.stepx + p.ew - p.margin;
@@ -557,6 +484,16 @@ dual3x3_kernel(const __grid_constant__ DualParams<T> p, const __grid_constant__ 
             }
         }
         DTRACE(7);
+        if (multi) {
+            // every message addressed to this tile in this round has been consumed by the warp that polls it: each warp leaves
+            // its own entries clean for the round after next / the next launch / graph replay
+            if (poll_col) { my_box[poll_col_idx] = make_uint4(0, 0, 0, 0); my_box[M::n + poll_col_idx] = make_uint4(0, 0, 0, 0); }
+            if (rim_t || rim_b) {
+#pragma unroll
+                for (int h = 0; h < kHaloY; ++h) { my_box[poll_row_idx + 32 * h] = make_uint4(0, 0, 0, 0); my_box[M::n + poll_row_idx + 32 * h] = make_uint4(0, 0, 0, 0); }
+            }
+            __threadfence();
+        }
     }
 }
 
@@ -692,11 +629,13 @@ extern "C" __attribute__((visibility("default"))) int cspn_debug_set_trace_dual(
 }
 #endif
 
+// Opt-in (CSPN_FWD_KERNEL=dual): measured on B200 this kernel is slower than the single-tile kernel on every BASELINE
+// shape (36.0 vs 28.2 us for 8 x 304x228, 940 vs 690 us for 32 x 1216x352; DESIGN.md section 3b has the trace).
 bool dual_supported(int B, int C, int H, int W, int iters, int ksize, int mode)
 {
     (void)mode;
-    static const bool off = [] { const char* e = getenv("CSPN_FWD_KERNEL"); return e && !strcmp(e, "single"); }();   // A/B knob
-    if (off || ksize != 3 || B < 1) return false;
+    static const bool on = [] { const char* e = getenv("CSPN_FWD_KERNEL"); return e && !strcmp(e, "dual"); }();
+    if (!on || ksize != 3 || B < 1) return false;
     if ((long)H * W > (1l << 30)) return false;
     if (((size_t)W * 2) % 16) return false;                 // TMA rows must be 16-byte multiples for both element sizes
     return plan_for(B, C, H, W, iters).ok;

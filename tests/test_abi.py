@@ -78,34 +78,48 @@ def test_workspace_queries():
 
 
 def test_planner_picks_kernel_and_workspace_by_problem_size():
-    """The workspace query runs the same planner as the launch (148 SMs / B200 cluster capacities as defaults without a
-    GPU).  3x3 forward with TMA-addressable rows (W % 8 == 0): dual-slot kernel, scratch = status word + two round
-    parities x CTAs x two slots of 16-byte-slot inboxes; other widths: the single-tile kernel (hardware clusters need no
-    scratch, stream mode one inbox per tile); the blocked 5x5 path two fp32 planes; the fused backward the per-SM history
+    """The workspace query runs the same planner as the launch (B200 cluster capacities as defaults without a GPU):
+    hardware clusters need no scratch, stream mode one 16-byte-slot inbox per tile (576 slots for a 64x80 tile) and only
+    when a whole image is resident at once, the blocked 5x5 path two fp32 planes, the fused backward the per-SM history
     (192 slots x T x 64 x 64 floats)."""
     lib = _lib.load()
-
-    def dual_ws(ctas, p):
-        return 256 + 2 * ctas * 2 * 2 * (2 * 4 * p + 4 * 32) * 16        # two parities of (2 TH + 128) messages, TH = 4 p
-
-    plan = _lib.forward_plan(8, 1, 228, 304, 24)                      # headline: 8 images x 35 tiles of 64x40 (4 warps x 10 rows), one round
-    assert plan == dict(kernel=_lib.KERNEL_DUAL, rows_per_warp=10, cx=5, cy=7, ntx=1, nty=1, ctas=140, rounds=1, units_per_class=4, units=8)
-    assert lib.cspn_fwd_workspace_bytes(8, 1, 228, 304, 24, 3, 0) >= dual_ws(140, 10)
-    plan = _lib.forward_plan(32, 1, 352, 1216, 24)                    # KITTI: half images of 21x7 tiles of 64x32, a round per image
-    assert (plan["kernel"], plan["rows_per_warp"], plan["ntx"] * plan["nty"], plan["rounds"]) == (_lib.KERNEL_DUAL, 8, 2, 32)
-    assert 140 <= plan["cx"] * plan["cy"] == plan["ctas"] <= 148
-    assert lib.cspn_fwd_workspace_bytes(32, 1, 352, 1216, 24, 3, 0) >= dual_ws(plan["ctas"], 8)
-    plan = _lib.forward_plan(1, 1, 1080, 1440, 24)                    # one image larger than the GPU: resident units with margins
-    assert plan["kernel"] == _lib.KERNEL_DUAL and plan["cx"] * plan["cy"] <= 148 and plan["ntx"] * plan["nty"] > 1
-    assert _lib.forward_plan(3, 1, 97, 131, 24)["kernel"] == _lib.KERNEL_SINGLE          # odd width: plain-load prologue kernel
+    inbox = (4 * 80 + 4 * 2 * 32) * 16
+    assert _lib.forward_plan(8, 1, 228, 304, 24)["kernel"] == _lib.KERNEL_SINGLE
+    assert lib.cspn_fwd_workspace_bytes(1, 1, 228, 304, 24, 3, 0) == 0                 # one 5x3 cluster: DSMEM
+    assert lib.cspn_fwd_workspace_bytes(7, 1, 228, 304, 24, 3, 0) == 0                 # 7 clusters of 15 fit at once
+    assert lib.cspn_fwd_workspace_bytes(8, 1, 228, 304, 24, 3, 0) == 8 * 15 * inbox    # the 8th would not: stream mode, 120 tiles
+    assert lib.cspn_fwd_workspace_bytes(32, 1, 352, 1216, 24, 3, 0) == 0               # KITTI batch: 4x2 hardware clusters
+    assert lib.cspn_fwd_workspace_bytes(8, 1, 64, 64, 24, 3, 0) == 0                   # single-tile images
+    # one image with more tiles than SMs (720p: 22 x 10 = 220): never the lockstep stream (it would wait on tiles that have
+    # not started), hardware clusters with margins instead
+    assert lib.cspn_fwd_workspace_bytes(1, 1, 720, 1280, 24, 3, 0) == 0
+    assert lib.cspn_fwd_workspace_bytes(2, 1, 1080, 1440, 24, 3, 0) == 0
+    assert lib.cspn_bwd_workspace_bytes(1, 1, 1080, 1920, 24, 3, 0) == 192 * 24 * 64 * 64 * 4          # backward: history only, no inboxes
     assert _lib.forward_plan(16, 1, 480, 640, 12, 5, 1)["kernel"] == _lib.KERNEL_BLOCKED
     assert _lib.forward_plan(1, 1, 20, 30, 4, 7, 1)["kernel"] == _lib.KERNEL_GENERIC
-    inbox = (4 * 80 + 4 * 2 * 32) * 16
-    assert lib.cspn_fwd_workspace_bytes(1, 1, 228, 302, 24, 3, 0) == 0                 # single-tile kernel, one 5x3 cluster: DSMEM
-    assert lib.cspn_fwd_workspace_bytes(8, 1, 228, 302, 24, 3, 0) == 8 * 15 * inbox    # the 8th cluster would not fit: stream mode
     assert lib.cspn_fwd_workspace_bytes(16, 1, 480, 640, 12, 5, 1) == 2 * 16 * 480 * 640 * 4
     assert lib.cspn_fwd_workspace_bytes(16, 1, 480, 640, 4, 5, 1) == 0                 # one launch: no hand-over planes
     hist = 192 * 24 * 64 * 64 * 4
     assert lib.cspn_bwd_workspace_bytes(1, 1, 60, 60, 24, 3, 0) == hist                # one tile: history only
     n = lib.cspn_bwd_workspace_bytes(8, 1, 228, 304, 24, 3, 0)
     assert n == hist + 8 * 20 * (4 * 64 + 4 * 2 * 32) * 16                             # stream mode: 20 tiles of 64x64 per image
+
+
+def test_dual_slot_planner_is_opt_in():
+    """The dual-slot forward kernel (CSPN_FWD_KERNEL=dual, read once per process): units of resident tiles, two per CTA."""
+    import subprocess
+    import sys
+    code = ("from cspn_monodepth_b200 import _lib\n"
+            "p = _lib.forward_plan(8, 1, 228, 304, 24)\n"
+            "assert p == dict(kernel=_lib.KERNEL_DUAL, rows_per_warp=10, cx=5, cy=7, ntx=1, nty=1, ctas=140, rounds=1, units_per_class=4, units=8), p\n"
+            "p = _lib.forward_plan(32, 1, 352, 1216, 24)\n"
+            "assert (p['kernel'], p['rows_per_warp'], p['ntx'] * p['nty'], p['rounds']) == (_lib.KERNEL_DUAL, 8, 2, 32) and p['ctas'] <= 148, p\n"
+            "p = _lib.forward_plan(1, 1, 1080, 1440, 24)\n"
+            "assert p['kernel'] == _lib.KERNEL_DUAL and p['cx'] * p['cy'] <= 148 and p['ntx'] * p['nty'] > 1, p\n"
+            "assert _lib.forward_plan(3, 1, 97, 131, 24)['kernel'] == _lib.KERNEL_SINGLE\n"
+            "n = _lib.load().cspn_fwd_workspace_bytes(8, 1, 228, 304, 24, 3, 0)\n"
+            "assert n >= 256 + 2 * 140 * 2 * 2 * (2 * 40 + 128) * 16, n\n")
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, CSPN_FWD_KERNEL="dual", PYTHONPATH=root), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr

@@ -261,21 +261,29 @@ def test_fused_backward_iteration_counts(iters):
     _check_backward(1, 8, (1, 70, 200), iters, seed=iters + 100, density=None if iters == 3 else 0.05)
 
 
-@pytest.mark.parametrize("exchange", ["global", "dsmem", "auto"])
+@pytest.mark.parametrize("exchange", ["global", "dsmem"])
 def test_forced_exchange_modes(exchange):
-    """Both halo transports of the single-tile fused kernels (forward with CSPN_FWD_KERNEL=single, and the backward) on
-    the same problems, fp32 and fp16 (the overrides are per process, hence the worker): stream mode with several tiles
-    per persistent CTA, hardware clusters with several cluster tiles per image.  "auto" runs the same worker with the
-    default planner, i.e. the dual-slot forward kernel wherever the guidance is TMA-addressable."""
+    """Both halo transports of the fused kernels on the same problems, fp32 and fp16 (the override is per process, hence
+    the worker): stream mode with several tiles per persistent CTA, hardware clusters with several cluster tiles per image."""
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ)
-    if exchange != "auto":
-        env.update(CSPN_EXCHANGE=exchange, CSPN_FWD_KERNEL="single")
+    env = dict(os.environ, CSPN_EXCHANGE=exchange)
     r = subprocess.run([sys.executable, os.path.join(root, "tests", "exchange_modes_worker.py")], env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok " + exchange), r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_dual_slot_forward_kernel():
+    """The opt-in dual-slot forward kernel (CSPN_FWD_KERNEL=dual, read once per process, hence the worker) over what its
+    planner produces, against the C oracle, plus CUDA-graph replay."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CSPN_FWD_KERNEL="dual")
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "dual_kernel_worker.py")], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok dual"), r.stdout[-2000:] + r.stderr[-4000:]
 
 
 def _fp16_case(seed, b, cg, h, w, density):
@@ -327,171 +335,3 @@ def test_single_image_larger_than_the_gpu(h, w):
     assert torch.isfinite(td.grad).all() and torch.isfinite(tg.grad).all()
     assert_close_nan(td.grad.cpu().numpy(), gd, GRAD_RTOL * max(1.0, np.abs(gd).max()), f"grad_depth 1x{h}x{w}")
     assert_close_nan(tg.grad.cpu().numpy(), gg, GRAD_RTOL * max(1.0, np.abs(gg).max()), f"grad_guidance 1x{h}x{w}")
-
-
-# The dual-slot forward kernel over what its planner produces: one unit (single slot, exposed refresh), odd unit counts
-# (last CTAs with one slot), several rounds, units cut with margins, mode OURS, fp16, several depth channels, no sparse.
-@pytest.mark.parametrize("mode,b,c,h,w,iters,density", [
-    (0, 1, 1, 228, 304, 24, 0.0072), (0, 7, 1, 228, 304, 24, 0.0072), (0, 19, 1, 228, 304, 24, 0.0072),
-    (1, 5, 1, 228, 304, 24, 0.02), (0, 3, 1, 352, 1216, 24, 0.05), (1, 1, 1, 480, 640, 24, 0.02),
-    (0, 2, 3, 120, 200, 9, 0.05), (0, 2, 1, 100, 72, 1, 0.05), (0, 2, 1, 100, 72, 2, 0.05), (0, 3, 1, 100, 136, 7, None),
-    (0, 40, 1, 96, 128, 5, 0.05), (1, 2, 1, 64, 64, 40, 0.05),
-])
-def test_dual_slot_forward_planner_grid(mode, b, c, h, w, iters, density):
-    g, d, s = make_inputs(b * h + w + iters, b, 8, c, h, w, density=density)
-    tg, td, ts = _cu(g), _cu(d), _cu(s)
-    y = cspn_new.AffinityPropagate(iters, 3)(tg, td, ts) if mode == 0 else cspn_ours.AffinityPropagate(prop_time=iters)(td, tg, sparse_depth=ts)
-    assert _lib.load().cspn_last_path() == _lib.PATH_FUSED and _lib.load().cspn_last_launch_count() == 1
-    ref = c_oracle.forward(g, d, s, iters, 3, mode, threads=0)
-    assert_close_nan(y.cpu().numpy(), ref, _atol(ref), f"dual mode {mode} {b}x{c}x{h}x{w} T {iters}")
-
-
-# ---- size-independent properties at BASELINE.json's full sizes -------------------------------
-@pytest.mark.parametrize("path", PATHS)
-def test_full_size_properties(path):
-    _lib.load().cspn_set_path(path)
-    for (b, h, w, dtype) in ((8, 228, 304, torch.float32), (4, 352, 1216, torch.float16)):
-        g, d, s = make_inputs(b * h, b, 8, 1, h, w, density=0.01)
-        y, _, _ = _run(0, g, d, s, 24, dtype=dtype)
-        yf = y.float()
-        assert torch.isfinite(yf).all()
-        assert yf.min().item() >= d.min() - 2e-2 and yf.max().item() <= d.max() + 2e-2      # convex combination
-        hit = torch.from_numpy(s > 0).to(DEV)
-        assert torch.equal(y[hit], _cu(d, dtype)[hit])                                        # blur depth re-injected exactly
-        # batch-slice independence, bit exact: the multi-GPU sharding property
-        y0, _, _ = _run(0, g[1:3], d[1:3], s[1:3], 24, dtype=dtype)
-        assert torch.equal(y0, y[1:3])
-        # constant depth is a fixed point; guidance scale invariance
-        const = np.full_like(d, 2.5)
-        yc, _, _ = _run(0, g, const, s, 24, dtype=dtype)
-        assert (yc.float() - 2.5).abs().max().item() < 1e-3
-        y2, _, _ = _run(0, g * np.float32(-2.0), d, s, 24, dtype=dtype)
-        assert (y2.float() - yf).abs().max().item() < (1e-4 if dtype == torch.float32 else 2e-2)
-
-
-def test_full_size_backward_properties():
-    """Oracle-free properties of the fused backward at BASELINE.json's full sizes: gradient mass
-    (sum of d(sum out)/d depth = number of pixels, mode A with a 0/1 mask), exact linearity in grad_out for a factor 2,
-    zero gradient for the guidance channels that are not read, and batch-slice independence bit for bit although the
-    full batch and the slice run with different tilings / halo transports."""
-    for (b, h, w, dtype) in ((8, 228, 304, torch.float32), (4, 352, 1216, torch.float32)):
-        g, d, s = make_inputs(7 * b + h, b, 12, 1, h, w, density=0.01)
-        y, tg, td = _run(0, g, d, s, 24, requires_grad=True, dtype=dtype)
-        assert _lib.load().cspn_last_path() == _lib.PATH_FUSED
-        y.backward(torch.ones_like(y))
-        assert _lib.load().cspn_last_path() == _lib.PATH_FUSED and _lib.load().cspn_last_launch_count() == 1
-        gd1, gg1 = td.grad.clone(), tg.grad.clone()
-        assert torch.isfinite(gd1).all() and torch.isfinite(gg1).all()
-        mass = gd1.double().sum().item()
-        assert abs(mass - b * h * w) <= 1e-4 * b * h * w, f"gradient mass {mass} vs {b * h * w}"
-        assert torch.count_nonzero(gg1[:, 8:]) == 0
-        go = torch.from_numpy(np.random.default_rng(b).standard_normal(d.shape).astype(np.float32)).to(DEV)
-        grads = []
-        for scale in (1.0, 2.0):
-            y, tg, td = _run(0, g, d, s, 24, requires_grad=True, dtype=dtype)
-            y.backward(go * scale)
-            grads.append((td.grad.clone(), tg.grad.clone()))
-        assert torch.equal(grads[1][0], grads[0][0] * 2) and torch.equal(grads[1][1], grads[0][1] * 2)
-        y, tg, td = _run(0, g[1:3], d[1:3], s[1:3], 24, requires_grad=True, dtype=dtype)
-        y.backward(go[1:3])
-        assert torch.equal(td.grad, grads[0][0][1:3]) and torch.equal(tg.grad, grads[0][1][1:3])
-
-
-def test_extra_and_strided_guidance_channels():
-    g, d, s = make_inputs(31, 2, 12, 1, 33, 47, density=0.05)
-    y12, _, _ = _run(0, g, d, s, 24)
-    y8, _, _ = _run(0, g[:, :8], d, s, 24)
-    assert torch.equal(y12, y8)
-    wide = _cu(g)
-    view = wide.narrow(1, 0, 8)                     # batch stride 12*H*W, no copy
-    y = cspn_new.AffinityPropagate(24, 3)(view, _cu(d), _cu(s))
-    assert torch.equal(y, y8)
-    nc = _cu(d).permute(0, 1, 3, 2).contiguous().permute(0, 1, 3, 2)   # non-contiguous depth gets copied
-    assert torch.equal(cspn_new.AffinityPropagate(24, 3)(view, nc, _cu(s)), y8)
-
-
-def test_inputs_not_modified_and_output_fresh():
-    g, d, s = make_inputs(41, 1, 8, 1, 20, 20, density=0.1)
-    tg, td, ts = _cu(g), _cu(d), _cu(s)
-    y = cspn_new.AffinityPropagate(5, 3)(tg, td, ts)
-    assert torch.equal(tg, _cu(g)) and torch.equal(td, _cu(d)) and torch.equal(ts, _cu(s))
-    assert y.data_ptr() != td.data_ptr()
-
-
-def test_raw_c_abi_pointers_and_errors():
-    lib = _lib.load()
-    g, d, s = make_inputs(51, 1, 8, 1, 24, 40, density=0.05)
-    tg, td, ts = _cu(g), _cu(d), _cu(s)
-    out = torch.empty_like(td)
-    n = lib.cspn_fwd_workspace_bytes(1, 1, 24, 40, 24, 3, 0)
-    ws = torch.empty(max(n, 1), dtype=torch.uint8, device=DEV)
-    stream = torch.cuda.current_stream().cuda_stream
-    rc = lib.cspn_fwd_f32(tg.data_ptr(), 8 * 24 * 40, td.data_ptr(), ts.data_ptr(), 1, out.data_ptr(), 1, 1, 24, 40, 24, 3, 0, ws.data_ptr(), n, stream)
-    assert rc == 0 and lib.cspn_last_launch_count() >= 1
-    torch.cuda.synchronize()
-    assert_close_nan(out.cpu().numpy(), c_oracle.forward(g, d, s, 24, 3, 0), FWD_ATOL, "raw abi")
-    lib.cspn_set_path(_lib.PATH_GENERIC)
-    rc = lib.cspn_fwd_f32(tg.data_ptr(), 8 * 24 * 40, td.data_ptr(), ts.data_ptr(), 1, out.data_ptr(), 1, 1, 24, 40, 24, 3, 0, None, 0, stream)
-    assert rc == -6                                  # generic path without workspace
-    with pytest.raises(RuntimeError):
-        cspn_new.AffinityPropagate(2, 3)(tg.double(), td.double())
-    with pytest.raises(RuntimeError):
-        cspn_new.AffinityPropagate(2, 3)(tg[:, :7], td)
-    with pytest.raises(RuntimeError):
-        cspn_new.AffinityPropagate(2, 3)(tg, td[:, :, :-1])
-
-
-def test_host_buffer_entry_point():
-    lib = _lib.load()
-    g, d, s = make_inputs(61, 2, 12, 1, 50, 70, density=0.05)
-    hg, hd, hs = (torch.from_numpy(a).pin_memory() for a in (g, d, s))
-    out = torch.empty_like(hd).pin_memory()
-    rc = lib.cspn_fwd_host_f32(hg.data_ptr(), 12 * 50 * 70, hd.data_ptr(), hs.data_ptr(), 1, out.data_ptr(), 2, 1, 50, 70, 24, 3, 0, None)
-    assert rc == 0
-    assert_close_nan(out.numpy(), c_oracle.forward(g, d, s, 24, 3, 0), FWD_ATOL, "host entry")
-
-
-def test_cuda_graph_capture_and_threads():
-    g, d, s = make_inputs(71, 2, 8, 1, 64, 96, density=0.05)
-    tg, td, ts = _cu(g), _cu(d), _cu(s)
-    mod = cspn_new.AffinityPropagate(24, 3)
-    eager = mod(tg, td, ts)
-    torch.cuda.synchronize()
-    graph = torch.cuda.CUDAGraph()
-    side = torch.cuda.Stream()
-    with torch.cuda.stream(side):
-        mod(tg, td, ts)
-        torch.cuda.synchronize()
-        with torch.cuda.graph(graph, stream=side):
-            captured = mod(tg, td, ts)
-    graph.replay(); torch.cuda.synchronize()
-    assert torch.equal(captured, eager)
-    results = [None] * 4
-
-    def work(i):
-        with torch.cuda.stream(torch.cuda.Stream()):
-            results[i] = mod(tg, td, ts)
-            torch.cuda.current_stream().synchronize()
-
-    threads = [threading.Thread(target=work, args=(i,)) for i in range(4)]
-    [t.start() for t in threads]; [t.join() for t in threads]
-    assert all(torch.equal(r, eager) for r in results)
-
-
-def test_end_to_end_training_step_through_module():
-    torch.manual_seed(0)
-    head = torch.nn.Conv2d(4, 9, 3, padding=1).to(DEV)                  # stands in for the UNet's two heads
-    x = torch.rand(2, 4, 40, 52, device=DEV)
-    sparse = (torch.rand(2, 1, 40, 52, device=DEV) < 0.05).float() * 3.0
-    target = torch.rand(2, 1, 40, 52, device=DEV) * 10
-    opt = torch.optim.SGD(head.parameters(), lr=1e-3)
-    cspn = cspn_new.AffinityPropagate(24, 3)
-    losses = []
-    for _ in range(3):
-        feat = head(x)
-        pred = cspn(feat[:, :8], feat[:, 8:9].abs() * 5, sparse)
-        loss = (pred - target).abs().mean()
-        opt.zero_grad(); loss.backward(); opt.step()
-        losses.append(loss.item())
-    assert all(np.isfinite(losses)) and losses[-1] < losses[0]
-    assert pkg.MODE_NEW == 0
