@@ -15,12 +15,17 @@ sets that their footprint exceeds the 126 MB L2, so every step reads its inputs 
 
 The JSON line also carries:
   roofline      dominant (only) kernel: algorithmic bytes per launch / measured launch time vs measured HBM peak
-  cpu_baseline  the reference's CPU path (op-for-op PyTorch port, oracle/torch_port.py) on the host cores
-  e2e           the same metric through the host-buffer C-ABI entry point (H2D + kernel + D2H per step)
-  extra         the other BASELINE sizes (KITTI 1216x352 fp16, 5x5 PAC variant) for context
+  cpu_baseline  the reference's CPU path on the host cores: the UNMODIFIED reference module staged under baseline/_ref
+                (baseline/fetch_ref.py; kind "reference") or, if that is missing, its op-for-op port oracle/torch_port.py
+  e2e           the same metric through the host-buffer C-ABI entry points (pinned host buffers; H2D + kernel + D2H of every
+                step inside the timed region; cspn_fwd_host_submit_* keeps three calls in flight)
+  max_abs       largest deviation of the timed configuration's output from the C oracle (BASELINE.json: "max-abs vs ref")
+  extra         the other BASELINE sizes (KITTI 1216x352 fp16 forward and forward+backward, 5x5 PAC variant, NYU
+                forward+backward) on every rank - aggregated over ranks like `value` - and context rows (eager launch cost,
+                the reference module itself on the B200)
 
-`--impl reference` times the reference's CPU implementation (the port; /root/reference does not exist on
-the GPU box) on the same config and prints the same line with "impl": "reference".
+`--impl reference` times the reference's own CPU implementation on the same config and prints the same line with
+"impl": "reference".
 """
 from __future__ import annotations
 
@@ -170,14 +175,20 @@ def run_module(cfg, sets):
     def step(i):
         g, d, s = sets[i % len(sets)]
         return mod(g, d, s) if cfg["mode"] == 0 else mod(d, g, sparse_depth=s)
+    step.inputs = sets
     return step
 
 
-def device_sets(cfg, dev, rank):
+def n_input_sets(cfg):
     px_bytes = BYTES_PER_PX[(cfg["dtype"], cfg["ksize"])] * cfg["B"] * cfg["H"] * cfg["W"]
     nsets = max(2, int(np.ceil(1.5 * L2_BYTES / px_bytes)))     # rotating footprint >= 1.5 x L2
     if os.environ.get("CSPN_BENCH_WARM_L2"):                    # experiments only
         nsets = 1
+    return nsets
+
+
+def device_sets(cfg, dev, rank):
+    nsets = n_input_sets(cfg)
     return [[t.to(dev) for t in synth(cfg, 1000 * rank + i)] for i in range(nsets)], nsets
 
 
@@ -276,33 +287,56 @@ def time_e2e(cfg, dev, steps, dist=None):
     cg = cfg["ksize"] ** 2 - 1
     stream = torch.cuda.current_stream(dev).cuda_stream
 
+    depth = lib.cspn_host_pipeline_depth()
+    sub = lib.cspn_fwd_host_submit_f32 if cfg["dtype"] == "f32" else lib.cspn_fwd_host_submit_f16
+    outs += [carve(sets[0][1]) for _ in range(max(0, depth - len(outs)))]
+    import ctypes
+    tickets = [ctypes.c_int(0) for _ in range(depth)]
+
     def call(i):
         g, d, s = sets[i % 2]
-        _lib.check(fn(g.data_ptr(), cg * h * w, d.data_ptr(), s.data_ptr(), 1, outs[i % 2].data_ptr(),
+        _lib.check(fn(g.data_ptr(), cg * h * w, d.data_ptr(), s.data_ptr(), 1, outs[i % depth].data_ptr(),
                       b, 1, h, w, cfg["iters"], cfg["ksize"], cfg["mode"], stream))
+
+    def run_pipelined(n):
+        """n calls with up to `depth` in flight; every result is waited for (it is in host memory) before its slot is reused."""
+        for i in range(n):
+            k = i % depth
+            if i >= depth:
+                _lib.check(lib.cspn_host_wait(tickets[k].value))
+            g, d, s = sets[i % 2]
+            _lib.check(sub(g.data_ptr(), cg * h * w, d.data_ptr(), s.data_ptr(), 1, outs[k].data_ptr(),
+                           b, 1, h, w, cfg["iters"], cfg["ksize"], cfg["mode"], ctypes.byref(tickets[k])))
+        for k in range(min(n, depth)):
+            _lib.check(lib.cspn_host_wait(tickets[k].value))
     for i in range(3):
         call(i)
+    run_pipelined(2 * depth)
+    check = float(outs[0].float().mean())
     torch.cuda.synchronize(dev)
     if dist is not None:
         dist.barrier()
-    blocks = []
-    for _ in range(3):                      # median of three blocks of `steps` calls: host-side copies are noisy on shared boxes
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(steps):
-            call(i)
-        e1.record()
-        torch.cuda.synchronize(dev)
-        blocks.append(e0.elapsed_time(e1) / steps)
-    ms = statistics.median(blocks)
-    if dist is not None:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+
+    def median_of_blocks(fn_block):
+        blocks = []
+        for _ in range(3):                  # median of three blocks of `steps` calls: host-side copies are noisy on shared boxes
+            t0 = time.perf_counter()
+            fn_block()
+            blocks.append((time.perf_counter() - t0) * 1e3 / steps)
+        ms = statistics.median(blocks)
+        if dist is not None:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+    # host wall clock: every call returns only when its result is in host memory (the timed region starts and ends with an
+    # idle device and fully delivered results, so wall time = device + copy time)
+    ms_sync = median_of_blocks(lambda: [call(i) for i in range(steps)])
+    ms_pipe = median_of_blocks(lambda: run_pipelined(steps))
     esz = sets[0][0].element_size()
     h2d = (cg + 2) * b * h * w * esz
     d2h = b * h * w * esz
-    return ms, h2d, d2h, float(outs[0].float().mean())
+    return ms_pipe, ms_sync, h2d, d2h, check, depth
 
 
 def time_fwd_bwd(cfg, dev, steps):
@@ -349,33 +383,48 @@ def time_fwd_bwd(cfg, dev, steps):
     return e0.elapsed_time(e1) / steps, launches[0]
 
 
-def cpu_reference(cfg, min_seconds=4.0, max_steps=8, batch=None):
-    """Reference CPU path (op-for-op port) on a bounded sample; returns dict for `cpu_baseline`."""
+def reference_forward(cfg):
+    """(callable(g, d, s) -> out, kind, description) of the reference's own implementation of the path: the UNMODIFIED module
+    from baseline/_ref (staged by baseline/fetch_ref.py) when it is there, else the op-for-op port."""
+    ref_root = os.path.join(ROOT, "baseline", "_ref")
+    if cfg["mode"] == 0 and os.path.isdir(os.path.join(ref_root, "network")):
+        if ref_root not in sys.path:
+            sys.path.insert(0, ref_root)
+        from network.libs.post_process import CSPN_new as ref_new          # the reference's own file, unmodified
+        mod = ref_new.AffinityPropagate(cfg["iters"], 3)
+        return (lambda g, d, s: mod(g, d, s)), "reference", "baseline/_ref/network/libs/post_process/CSPN_new.py (the unmodified reference module)"
     from oracle import torch_port
+    if cfg["mode"] == 0:
+        return (lambda g, d, s: torch_port.mode_a_forward(g, d, s, cfg["iters"])), "port", "oracle/torch_port.py (op-for-op PyTorch restatement of CSPN_new.py:26-128)"
+    return (lambda g, d, s: torch_port.mode_b_forward(d, g, s, cfg["iters"])), "port", "oracle/torch_port.py (op-for-op PyTorch restatement of CSPN_ours.py:24-54)"
+
+
+def cpu_reference(cfg, min_seconds=4.0, max_steps=8, min_steps=5, batch=None, threads=None):
+    """Reference CPU path on a bounded sample; returns (dict for `cpu_baseline`, list of step times)."""
     b = batch or cfg["B"]
     small = dict(cfg, B=b, dtype="f32")                 # the reference is fp32-only (CSPN_new.py:122)
     g, d, s = synth(small, 5)
-    fwd = (lambda: torch_port.mode_a_forward(g, d, s, cfg["iters"])) if cfg["mode"] == 0 else (lambda: torch_port.mode_b_forward(d, g, s, cfg["iters"]))
+    fn, kind, what = reference_forward(cfg)
+    fwd = lambda: fn(g, d, s)
     cores = os.cpu_count() or 1
     best = None
     with torch.no_grad():
-        for threads in sorted({1, max(1, cores // 2), cores}):
-            torch.set_num_threads(threads)
+        for t in ([threads] if threads else sorted({1, max(1, cores // 2), cores})):
+            torch.set_num_threads(t)
             fwd()
             t0 = time.perf_counter(); fwd(); dt = time.perf_counter() - t0
             if best is None or dt < best[1]:
-                best = (threads, dt)
+                best = (t, dt)
         torch.set_num_threads(best[0])
         times = []
         t_start = time.perf_counter()
-        while len(times) < max_steps and (len(times) < 3 or time.perf_counter() - t_start < min_seconds):
+        while len(times) < max_steps and (len(times) < min_steps or time.perf_counter() - t_start < min_seconds):
             t0 = time.perf_counter(); fwd(); times.append(time.perf_counter() - t0)
     px = b * cfg["H"] * cfg["W"]
     med = statistics.median(times)
-    return {"value": px / med / 1e6, "unit": UNIT, "cores": best[0], "host_cores": cores, "kind": "port",
-            "sample": f"{len(times)} forwards of batch {b} x {cfg['H']}x{cfg['W']} fp32, {cfg['iters']} iterations, "
-                      f"oracle/torch_port.py (op-for-op PyTorch restatement of CSPN_new.py:26-128), torch {torch.__version__}, "
-                      f"{best[0]} threads (fastest of 1/{max(1, cores // 2)}/{cores})",
+    return {"value": px / med / 1e6, "unit": UNIT, "cores": best[0], "host_cores": cores, "kind": kind,
+            "sample": f"{len(times)} forwards of batch {b} x {cfg['W']}x{cfg['H']} fp32, {cfg['iters']} iterations, {what}, torch {torch.__version__}, "
+                      + (f"{best[0]} threads" if threads else f"{best[0]} threads (fastest of 1/{max(1, cores // 2)}/{cores})"),
             "ms_per_step": med * 1e3}, times
 
 
@@ -390,26 +439,129 @@ def cpu_c_oracle(cfg):
 
 
 def main_reference(args, rank):
+    """The reference's own CPU implementation on the bench configuration: W warm-up + K timed forwards (K >= 5 so that the
+    median is one), each a bounded sample = one batch of the workload; rank 0 only."""
     if rank != 0:
         return
     cfg = NYU
-    res, times = cpu_reference(cfg, min_seconds=0.0, max_steps=max(1, args.steps) + max(0, args.warmup))
-    times = times[max(0, min(args.warmup, len(times) - 1)):]
+    steps, warm = max(5, args.steps if args.steps < 2000 else 5), max(0, min(args.warmup, 3))
+    steps = min(steps, 20)                               # ~0.25 s per forward: the whole arm stays within a minute
+    res, times = cpu_reference(cfg, min_seconds=0.0, max_steps=steps + warm, min_steps=steps + warm)
+    times = times[warm:]
     ms = statistics.median(times) * 1e3
     value = cfg["B"] * cfg["H"] * cfg["W"] / (ms * 1e-3) / 1e6
     res["value"] = value
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup,
+    res["ms_per_step"] = ms
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times), "warmup": warm,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(cfg, 1), "cpu_baseline": res,
+            "config": workload_config(cfg, n_input_sets(cfg)), "cpu_baseline": res,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
 def workload_config(cfg, nsets):
-    return {"workload": f"batch {cfg['B']} x {cfg['W']}x{cfg['H']} (NYU shape), 3x3, {cfg['iters']} iterations, fp32, forward only, "
-                        f"mode CSPN_new, per GPU", "per_gpu_batch": cfg["B"], "height": cfg["H"], "width": cfg["W"], "iters": cfg["iters"],
-            "l2_policy": f"inputs rotate over {nsets} independent sets ({nsets} x 24.4 MB > 126 MB L2)", "sharding": "independent batch slices, no collective",
+    es = 4 if cfg["dtype"] == "f32" else 2
+    mb = BYTES_PER_PX[(cfg["dtype"], cfg["ksize"])] * cfg["B"] * cfg["H"] * cfg["W"] / 1e6
+    return {"workload": f"batch {cfg['B']} x {cfg['W']}x{cfg['H']}, {cfg['ksize']}x{cfg['ksize']}, {cfg['iters']} iterations, fp{8 * es}, forward only, "
+                        f"mode {'CSPN_new' if cfg['mode'] == 0 else 'CSPN_ours'}, per GPU (BASELINE.json configs[1])",
+            "per_gpu_batch": cfg["B"], "height": cfg["H"], "width": cfg["W"], "iters": cfg["iters"],
+            "l2_policy": f"inputs rotate over {nsets} independent sets ({nsets} x {mb:.1f} MB > 126 MB L2)", "sharding": "independent batch slices, no collective",
             "launch": "timed steps replayed from CUDA graphs (one kernel launch per step)"}
+
+
+def max_abs_vs_oracle(cfg, dev):
+    """Largest |ours - oracle| over the whole output of the bench configuration (one input set), and the gradient errors of
+    forward + backward relative to the largest entry (BASELINE.json metric: "max-abs vs ref"; target 1e-4)."""
+    from oracle import c_oracle
+    g, d, s = synth(cfg, 1000)
+    step = run_module(cfg, [[t.to(dev).requires_grad_(i < 2) for i, t in enumerate((g, d, s))]])
+    y = step(0)
+    go = torch.randn(d.shape, generator=torch.Generator().manual_seed(9)).to(d.dtype)
+    y.backward(go.to(dev))
+    f32 = [t.float().numpy() for t in (g, d, s, go)]
+    ref = c_oracle.forward(f32[0], f32[1], f32[2], cfg["iters"], cfg["ksize"], cfg["mode"], threads=0)
+    out = {"max_abs": float(np.abs(y.detach().float().cpu().numpy() - ref).max()), "oracle": "oracle/cspn_oracle.c on the same inputs (pinned to reference-run goldens)"}
+    if cfg["ksize"] == 3:
+        gg, gd = c_oracle.backward(f32[0], f32[1], f32[2], f32[3], cfg["iters"], 3, cfg["mode"], threads=0)
+        tg, td = step.inputs[0][0].grad, step.inputs[0][1].grad
+        out["grad_depth_rel"] = float(np.abs(td.float().cpu().numpy() - gd).max() / max(1.0, np.abs(gd).max()))
+        out["grad_guidance_rel"] = float(np.abs(tg.float().cpu().numpy() - gg).max() / max(1.0, np.abs(gg).max()))
+    return out
+
+
+def time_eager(cfg, dev, steps=200):
+    """Per-call time when every step is launched from Python (no CUDA graph): what an eager training loop pays."""
+    sets, _ = device_sets(cfg, dev, 0)
+    step = run_module(cfg, sets)
+    with torch.no_grad():
+        for i in range(10):
+            step(i)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            step(i)
+        e1.record()
+        torch.cuda.synchronize(dev)
+    return e0.elapsed_time(e1) / steps
+
+
+def time_reference_on_gpu(cfg, dev, steps=5):
+    """Context row: the UNMODIFIED reference module (baseline/_ref) run on the B200 itself (`.cuda()` tensors, ~500 ATen
+    launches per forward) - the only apples-to-apples GPU comparison.  None when the reference is not staged."""
+    fn, kind, what = reference_forward(cfg)
+    if kind != "reference":
+        return None
+    g, d, s = [t.to(dev) for t in synth(dict(cfg, dtype="f32"), 1000)]
+    with torch.no_grad():
+        for _ in range(2):
+            y = fn(g, d, s)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            y = fn(g, d, s)
+        e1.record()
+        torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    ours = run_module(cfg, [[g, d, s]])(0)
+    return {"value": cfg["B"] * cfg["H"] * cfg["W"] / (ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms, "what": what + " on cuda:0, eager, L2-warm inputs",
+            "max_abs_vs_ours": float((y - ours).abs().max())}
+
+
+def extra_rows(dev, rank, world, dist, peak):
+    """The other BASELINE sizes on every rank at once (weak scaling: each rank its own batch), aggregated over ranks."""
+    extra = {}
+
+    def agg(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    for name, c, st in (("kitti_b32_1216x352_f16_fwd", KITTI, 30), ("pac5x5_b16_640x480_f32_fwd", PAC5, 10)):
+        try:
+            ms, ln, ns = time_device(c, dev, rank, st, 3, dist)
+            px = c["B"] * c["H"] * c["W"]
+            gbs = BYTES_PER_PX[(c["dtype"], c["ksize"])] * px / (ms / st * 1e-3) / 1e9
+            extra[name] = {"value": world * px / (ms / st * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms / st, "launches_per_step": ln,
+                           "roofline_frac": gbs / peak, "input_sets": ns, "n_gpus": world, "per_gpu_batch": c["B"]}
+        except Exception as exc:        # context numbers must not take the headline down
+            extra[name] = {"error": repr(exc)[:200]}
+        torch.cuda.empty_cache()
+    # forward + backward (BASELINE.json configs[2] is forward+backward): algorithmic bytes 11 + 20 elements per pixel
+    for name, c, st in (("kitti_b32_1216x352_f16_fwd_bwd", KITTI, 10), ("nyu_b8_304x228_f32_fwd_bwd", NYU, 100)):
+        try:
+            ms, ln = time_fwd_bwd(c, dev, st)
+            ms = agg(ms)
+            px = c["B"] * c["H"] * c["W"]
+            es = 4 if c["dtype"] == "f32" else 2
+            extra[name] = {"value": world * px / (ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms, "launches_per_step": ln,
+                           "roofline_frac": 31 * es * px / (ms * 1e-3) / 1e9 / peak, "n_gpus": world, "per_gpu_batch": c["B"]}
+        except Exception as exc:
+            extra[name] = {"error": repr(exc)[:200]}
+        torch.cuda.empty_cache()
+    return extra
 
 
 def main():
@@ -435,48 +587,47 @@ def main():
     px_step = cfg["B"] * cfg["H"] * cfg["W"]
     value = world * px_step / (ms_step * 1e-3) / 1e6
     # end-to-end leg on every rank at once (each GPU has its own PCIe link); the slowest rank sets the time
-    e_ms, h2d, d2h, _ = time_e2e(cfg, dev, min(args.steps, 50), dist)
+    e_ms, e_sync_ms, h2d, d2h, _, depth = time_e2e(cfg, dev, min(args.steps, 50), dist)
+    peak, peak_src = hbm_peak()
+    extra = None if args.no_extra else extra_rows(dev, rank, world, dist, peak)      # every rank runs them (aggregated over ranks)
     if rank == 0:
-        peak, peak_src = hbm_peak()
         alg_bytes = BYTES_PER_PX[(cfg["dtype"], cfg["ksize"])] * px_step
         achieved = alg_bytes / (ms_step * 1e-3) / 1e9
+        from cspn_monodepth_b200 import _lib
+        plan = _lib.forward_plan(cfg["B"], 1, cfg["H"], cfg["W"], cfg["iters"], cfg["ksize"], cfg["mode"])
+        kernel = {1: "cspn::fused3x3_kernel<float,10,8,CSPN_new> (single 64x80 tile per CTA)", 2: "cspn::dual3x3_kernel<float,10,CSPN_new> (two 64x40 tiles per CTA)"}.get(plan["kernel"], "?")
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(cfg, nsets), "gpu_launches": launches * args.steps,
                 "clocks": sampler.summary(),
-                "roofline": {"bound": "hbm", "kernel": "cspn::fused3x3_kernel<float,10,8,CSPN_new>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": ncu_traffic("nyu_b8_f32"), "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": alg_bytes, "launch_us": ms_step * 1e3,
                              "fma_floor_us": px_step * cfg["iters"] * 8 / (148 * 128 * 1.965e9) * 1e6}}
         line["e2e"] = {"value": world * px_step / (e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                       "ms_per_step": e_ms, "api": "cspn_fwd_host_f32 (C ABI, host buffers in one pinned staging arena), one call per rank and step",
+                       "ms_per_step": e_ms,
+                       "api": f"cspn_fwd_host_submit_f32 + cspn_host_wait (C ABI, host buffers in one pinned staging arena), {depth} calls in flight per rank: "
+                              "the H2D copy of a call overlaps the kernel and the D2H copy of the previous one; every result is waited for in host memory",
+                       "timing": "host wall clock around blocks of calls that start and end with an idle device (median of 3 blocks, max over ranks)",
+                       "sync_call": {"value": world * px_step / (e_sync_ms * 1e-3) / 1e6, "ms_per_step": e_sync_ms, "api": "cspn_fwd_host_f32, one blocking call per step"},
                        "n_gpus": world, "host_binding": numa}
+        try:
+            line["max_abs"] = max_abs_vs_oracle(cfg, dev)
+        except Exception as exc:
+            line["max_abs"] = {"error": repr(exc)[:200]}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"], _ = cpu_reference(cfg)
             line["cpu_baseline_fused_c"] = cpu_c_oracle(cfg)
-        if world == 1 and not args.no_extra:
-            extra = {}
-            for name, c, st in (("kitti_b32_1216x352_f16_fwd", KITTI, 30), ("pac5x5_b16_640x480_f32_fwd", PAC5, 10)):
+            # BASELINE.json configs[0]: the reference's own CPU-runnable case (B = 1), one thread and all cores
+            cores = os.cpu_count() or 1
+            line["cpu_cfg1"] = {f"{t}_threads": cpu_reference(cfg, min_seconds=1.0, max_steps=10, min_steps=5, batch=1, threads=t)[0] for t in sorted({1, cores})}
+        if extra is not None:
+            if world == 1:
                 try:
-                    ms, ln, ns = time_device(c, dev, rank, st, 3)
-                    px = c["B"] * c["H"] * c["W"]
-                    gbs = BYTES_PER_PX[(c["dtype"], c["ksize"])] * px / (ms / st * 1e-3) / 1e9
-                    extra[name] = {"value": px / (ms / st * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms / st, "launches_per_step": ln,
-                                   "roofline_frac": gbs / peak, "input_sets": ns}
-                except Exception as exc:        # context numbers must not take the headline down
-                    extra[name] = {"error": repr(exc)[:200]}
-                torch.cuda.empty_cache()
-            # forward + backward (BASELINE.json configs[2] is forward+backward): algorithmic bytes 11 + 20 elements per pixel
-            for name, c, st in (("kitti_b32_1216x352_f16_fwd_bwd", KITTI, 10), ("nyu_b8_304x228_f32_fwd_bwd", NYU, 100)):
-                try:
-                    ms, ln = time_fwd_bwd(c, dev, st)
-                    px = c["B"] * c["H"] * c["W"]
-                    es = 4 if c["dtype"] == "f32" else 2
-                    extra[name] = {"value": px / (ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms, "launches_per_step": ln,
-                                   "roofline_frac": 31 * es * px / (ms * 1e-3) / 1e9 / peak}
+                    extra["eager_launch_us_per_call"] = {"value": time_eager(cfg, dev) * 1e3, "what": "nn.Module forward launched from Python every step (no CUDA graph), same workload"}
+                    extra["reference_module_on_b200"] = time_reference_on_gpu(cfg, dev)
                 except Exception as exc:
-                    extra[name] = {"error": repr(exc)[:200]}
-                torch.cuda.empty_cache()
+                    extra["context_error"] = repr(exc)[:200]
             line["extra"] = extra
         print(json.dumps(line), flush=True)
     if dist is not None:

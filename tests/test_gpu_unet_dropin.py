@@ -1,0 +1,91 @@
+"""The reference's own UNets with the B200 module dropped in (SURVEY.md 8b / VERDICT r1 item 7): builds the unmodified
+`network/unet_cspn_nyu.py` and `network/unet_ours.py` from the staged reference (baseline/_ref, see baseline/fetch_ref.py -
+/root/reference itself does not exist on the GPU box), swaps `post_process_layer` with `dropin.patch_model`, and compares the
+whole network's output and one training step's gradients with the un-patched model on the same GPU and the same weights.
+
+Tolerance: the two runs share every cuDNN kernel up to the CSPN module; the module's own deviation is <= 1e-4 at depth
+scale 10.  Output: 1e-4 of the output range.  Gradients: the backward of the ResNet-50 encoder amplifies rounding noise, so
+they are compared per parameter tensor relative to that tensor's largest entry (1e-3) and additionally as a cosine similarity
+over all parameters (> 0.9999).
+"""
+import copy
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from cspn_monodepth_b200 import _lib, cspn_new, cspn_ours, dropin
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "baseline", "_ref")
+DEV = "cuda:0"
+
+
+def _import_reference():
+    if not os.path.isdir(os.path.join(REF, "network")):
+        pytest.skip("baseline/_ref is not staged (run `python baseline/fetch_ref.py` where /root/reference is mounted)")
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_golden import _install_thnn_shim              # pac.py:20 imports the removed torch._thnn
+    _install_thnn_shim()
+    from network import unet_cspn_nyu, unet_ours
+    return unet_cspn_nyu, unet_ours
+
+
+def _rgbd(batch, seed):
+    g = torch.Generator().manual_seed(seed)
+    rgb = torch.rand(batch, 3, 228, 304, generator=g)
+    dense = torch.rand(batch, 1, 228, 304, generator=g) * 9 + 0.5
+    mask = torch.rand(batch, 1, 228, 304, generator=g) < 500.0 / 69312.0
+    target = torch.rand(batch, 1, 228, 304, generator=g) * 10
+    return torch.cat([rgb, dense * mask], dim=1).to(DEV), target.to(DEV)      # the reference's rgbd input: channel 3 = sparse depth
+
+
+@pytest.mark.parametrize("which", ["unet_cspn_nyu", "unet_ours"])
+def test_reference_unet_with_b200_module(which):
+    unet_cspn_nyu, unet_ours = _import_reference()
+    torch.manual_seed(7)
+    torch.backends.cudnn.benchmark = False
+    torch.backends.cudnn.deterministic = True
+    ref_model = (unet_cspn_nyu if which == "unet_cspn_nyu" else unet_ours).resnet50(pretrained=False).to(DEV).train()
+    our_model = copy.deepcopy(ref_model)
+    assert dropin.patch_model(our_model) == 1
+    assert isinstance(our_model.post_process_layer, (cspn_new.AffinityPropagate, cspn_ours.AffinityPropagate))
+    assert type(ref_model.post_process_layer).__module__.startswith("network.libs.post_process")
+    assert our_model.state_dict().keys() == ref_model.state_dict().keys()       # the module has no parameters or buffers
+    x, target = _rgbd(2, 3)
+    outs, grads = [], []
+    for model in (ref_model, our_model):
+        model.zero_grad(set_to_none=True)
+        y = model(x)
+        if isinstance(y, (list, tuple)):                                        # unet_ours.py:335 returns [depth, guidance]
+            y = y[0]
+        if model is our_model:
+            assert _lib.load().cspn_last_path() == _lib.PATH_FUSED
+        valid = target > 0
+        loss = (y - target)[valid].abs().mean()                                 # MaskedL1Loss (libs/criterion/criteria.py:27-39)
+        loss.backward()
+        if model is our_model:
+            assert _lib.load().cspn_last_path() == _lib.PATH_FUSED and _lib.load().cspn_last_launch_count() == 1
+        outs.append(y.detach().float())
+        grads.append({n: p.grad.detach().float().clone() for n, p in model.named_parameters() if p.grad is not None})
+    assert torch.isfinite(outs[1]).all()
+    span = float(outs[0].abs().max())
+    err = float((outs[0] - outs[1]).abs().max())
+    assert err <= 1e-4 * max(1.0, span), f"{which}: output max-abs {err:.3e} (range {span:.3e})"
+    assert grads[0].keys() == grads[1].keys() and len(grads[0]) > 100
+    dot = sum(float((grads[0][n] * grads[1][n]).sum()) for n in grads[0])
+    n0 = sum(float((grads[0][n] ** 2).sum()) for n in grads[0]) ** 0.5
+    n1 = sum(float((grads[1][n] ** 2).sum()) for n in grads[0]) ** 0.5
+    assert dot / (n0 * n1) > 0.9999, f"{which}: gradient cosine {dot / (n0 * n1):.6f}"
+    worst = max((float((grads[0][n] - grads[1][n]).abs().max()) / max(float(grads[0][n].abs().max()), 1e-12), n) for n in grads[0])
+    assert worst[0] <= 1e-3, f"{which}: parameter {worst[1]} gradient differs by {worst[0]:.3e} of its largest entry"
+    # one optimiser step on both keeps the weights together
+    for model in (ref_model, our_model):
+        torch.optim.SGD(model.parameters(), lr=1e-3).step()
+    drift = max(float((p - q).abs().max()) for p, q in zip(ref_model.parameters(), our_model.parameters()))
+    assert np.isfinite(drift) and drift <= 1e-5
