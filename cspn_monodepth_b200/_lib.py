@@ -38,7 +38,7 @@ SIGNATURES = {
 PATH_AUTO, PATH_GENERIC, PATH_FUSED, PATH_BLOCKED = 0, 1, 2, 3
 MODE_NEW, MODE_OURS = 0, 1
 
-_lock = threading.Lock()
+_lock = threading.RLock()        # torch_ops() loads the C-ABI library while holding it
 _lib = None
 
 
@@ -88,6 +88,35 @@ def forward_plan(b: int, c: int, h: int, w: int, iters: int, ksize: int = 3, mod
     check(load().cspn_fwd_plan(b, c, h, w, iters, ksize, mode, buf))
     keys = ("kernel", "rows_per_warp", "cx", "cy", "ntx", "nty", "ctas", "rounds", "units_per_class", "units")
     return dict(zip(keys, list(buf)))
+
+
+_torch_ext = None
+
+
+def torch_ops():
+    """``torch.ops.cspn`` (the TORCH_LIBRARY layer, csrc/torch_ext.cpp) or None when ``CSPN_TORCH_EXT=0`` or it cannot be
+    built / loaded (no g++ and no prebuilt file): the operators then go through ctypes - same library, same kernels."""
+    global _torch_ext
+    if _torch_ext is None:
+        with _lock:
+            if _torch_ext is None:
+                _torch_ext = False
+                if os.environ.get("CSPN_TORCH_EXT", "1") != "0":
+                    try:
+                        import torch
+                        try:
+                            if _build.torch_ext_needs_build():
+                                _build.build_torch_ext()
+                        except Exception:
+                            if not os.path.exists(_build.TORCH_SO):
+                                raise
+                        load()                                          # libcspn_b200.so first (rpath $ORIGIN resolves it anyway)
+                        torch.ops.load_library(_build.TORCH_SO)
+                        _torch_ext = torch.ops.cspn
+                    except Exception as exc:                            # noqa: BLE001 - optional layer
+                        import warnings
+                        warnings.warn(f"libcspn_torch.so unavailable ({exc}); using the ctypes binding of libcspn_b200.so")
+    return _torch_ext or None
 
 
 def check(code: int) -> None:

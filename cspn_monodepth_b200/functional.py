@@ -111,6 +111,18 @@ def cspn_propagate(guidance, depth, sparse_depth=None, *, iters: int, ksize: int
     """
     if iters == 0:
         return depth
+    ops = _lib.torch_ops()
+    if ops is not None:
+        # C++ operator layer (TORCH_LIBRARY(cspn, ...), csrc/torch_ext.cpp): same checks, allocation and autograd formula
+        # as _CspnPropagate below, without the ctypes / Python overhead per call
+        for name, t in (("guidance", guidance), ("depth", depth), ("sparse_depth", sparse_depth)):
+            if t is None:
+                continue
+            if not isinstance(t, torch.Tensor):
+                raise TypeError(f"{name} must be a torch.Tensor")
+            if not t.is_cuda:
+                raise RuntimeError(f"{name} is on {t.device}: the B200 CSPN operator is CUDA-only and has no CPU fallback")
+        return ops.propagate(guidance, depth, sparse_depth, int(iters), int(ksize), int(mode))
     return _CspnPropagate.apply(guidance, depth, sparse_depth, int(iters), int(ksize), int(mode))
 
 

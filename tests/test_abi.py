@@ -123,3 +123,18 @@ def test_dual_slot_planner_is_opt_in():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, CSPN_FWD_KERNEL="dual", PYTHONPATH=root), capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_torch_library_layer_registers_the_operators():
+    """TORCH_LIBRARY(cspn, ...) (csrc/torch_ext.cpp, built in-tree as lib/libcspn_torch.so): the three operators exist with the
+    schemas SURVEY.md 8b lists, and CPU tensors are refused loudly (no CPU implementation anywhere in the product)."""
+    import torch
+    ops = _lib.torch_ops()
+    assert ops is not None, "libcspn_torch.so could not be built / loaded"
+    assert str(torch.ops.cspn.propagate.default._schema) == "cspn::propagate(Tensor guidance, Tensor depth, Tensor? sparse, int iters, int ksize, int mode) -> Tensor"
+    assert str(torch.ops.cspn.backward.default._schema).endswith("-> (Tensor, Tensor)")
+    g, d = torch.zeros(1, 8, 4, 4), torch.zeros(1, 1, 4, 4)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        torch.ops.cspn.forward(g, d, None, 2, 3, 0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        torch.ops.cspn.backward(d, g, d, None, 2, 3, 0)

@@ -335,3 +335,67 @@ def test_single_image_larger_than_the_gpu(h, w):
     assert torch.isfinite(td.grad).all() and torch.isfinite(tg.grad).all()
     assert_close_nan(td.grad.cpu().numpy(), gd, GRAD_RTOL * max(1.0, np.abs(gd).max()), f"grad_depth 1x{h}x{w}")
     assert_close_nan(tg.grad.cpu().numpy(), gg, GRAD_RTOL * max(1.0, np.abs(gg).max()), f"grad_guidance 1x{h}x{w}")
+
+
+def test_torch_library_ops_match_the_ctypes_path():
+    """The C++ operator layer (torch.ops.cspn.*, the default route of the nn.Modules) against the ctypes autograd.Function
+    over the same C ABI: bit-identical results and gradients, None / 1-channel / C-channel sparse, fp16, strided guidance,
+    errors as RuntimeError."""
+    from cspn_monodepth_b200 import functional
+    ops = _lib.torch_ops()
+    assert ops is not None
+    for mode, cg, c, dtype, sc in ((0, 12, 1, torch.float32, 1), (1, 8, 1, torch.float32, None), (0, 8, 3, torch.float16, 3), (1, 24, 1, torch.float32, 1)):
+        k = 5 if cg == 24 else 3
+        g, d, s = make_inputs(cg + c, 2, cg, c, 70, 96, density=None if sc is None else 0.05, sparse_channels=sc or 1)
+        res = []
+        for use_ops in (True, False):
+            tg, td, ts = _cu(g, dtype).requires_grad_(True), _cu(d, dtype).requires_grad_(True), _cu(s, dtype)
+            y = ops.propagate(tg, td, ts, 12, k, mode) if use_ops else functional._CspnPropagate.apply(tg, td, ts, 12, k, mode)
+            y.backward(torch.ones_like(y))
+            res.append((y.detach(), tg.grad, td.grad))
+        for a, b in zip(*res):
+            assert torch.equal(a, b)
+    wide = _cu(make_inputs(3, 2, 12, 1, 33, 48)[0])
+    d, s = _cu(make_inputs(3, 2, 12, 1, 33, 48)[1]), _cu(make_inputs(3, 2, 12, 1, 33, 48)[2])
+    assert torch.equal(ops.forward(wide.narrow(1, 0, 8), d, s, 24, 3, 0), ops.forward(wide[:, :8].contiguous(), d, s, 24, 3, 0))
+    with pytest.raises(RuntimeError):
+        ops.forward(wide[:, :7], d, s, 24, 3, 0)
+    with pytest.raises(RuntimeError):
+        ops.forward(wide, d, s, 24, 5, 0)                               # CSPN_new only works with prop_kernel 3
+    with torch.no_grad():
+        assert ops.propagate(wide, d, s, 0, 3, 0) is d or torch.equal(ops.propagate(wide, d, s, 0, 3, 0), d)
+
+
+def test_two_gpu_threaded_replicas():
+    """The reference's DataParallel pattern (network/libs/base/encoding.py:102-105): one Python thread per GPU, each calling
+    the module on its own batch slice at the same time.  Needs two devices (gpurun --gpus 2); results must equal the
+    single-device run bit for bit."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    g, d, s = make_inputs(91, 8, 12, 1, 228, 304, density=0.0072)
+    go = np.random.default_rng(4).standard_normal(d.shape).astype(np.float32)
+    y_full, tg_full, td_full = _run(0, g, d, s, 24, requires_grad=True)
+    y_full.backward(_cu(go))
+    results = [None, None]
+
+    def replica(i):
+        dev = torch.device("cuda", i)
+        sl = slice(4 * i, 4 * i + 4)
+        with torch.cuda.device(dev):
+            tg = torch.from_numpy(g[sl]).to(dev).requires_grad_(True)
+            td = torch.from_numpy(d[sl]).to(dev).requires_grad_(True)
+            ts = torch.from_numpy(s[sl]).to(dev)
+            mod = cspn_new.AffinityPropagate(24, 3)
+            for _ in range(5):                                          # several calls: per-device caches are hit concurrently
+                y = mod(tg, td, ts)
+            y.backward(torch.from_numpy(go[sl]).to(dev))
+            torch.cuda.synchronize(dev)
+            results[i] = (y.detach().cpu(), tg.grad.cpu(), td.grad.cpu())
+
+    threads = [threading.Thread(target=replica, args=(i,)) for i in range(2)]
+    [t.start() for t in threads]; [t.join() for t in threads]
+    for i in range(2):
+        sl = slice(4 * i, 4 * i + 4)
+        assert results[i] is not None
+        assert torch.equal(results[i][0], y_full.detach().cpu()[sl])
+        assert torch.equal(results[i][1], tg_full.grad.cpu()[sl]) and torch.equal(results[i][2], td_full.grad.cpu()[sl])
