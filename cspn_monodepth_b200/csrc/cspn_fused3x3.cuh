@@ -205,6 +205,7 @@ struct FusedParams {
     const T* gout;        // dL/d out
     T* gg; T* gd;         // dL/d guidance [B, Cg, H, W], dL/d depth [B, 1, H, W]
     int Cg;
+    int Ctot, ch0;        // backward works on depth channel ch0 of Ctot (one launch per channel; the forward takes all planes at once)
     float* hist;          // history scratch: hist_slots tiles of iters x TH x 64 floats, one per SM id
     int hist_slots;
 };
@@ -291,7 +292,8 @@ __device__ __forceinline__ void fused_tile(const FusedParams<T>& p, const CUtens
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ccx = bx % p.cx, ccy = by % p.cy;
     const int tix = bx / p.cx, tiy = by / p.cy;
-    const int plane = bz, b = plane / p.C, ch = plane - b * p.C;
+    const int plane = bz, b = plane / p.C, ch = BWD ? p.ch0 : plane - b * p.C;
+    const size_t dplane = BWD ? (size_t)b * p.Ctot + p.ch0 : (size_t)plane;      // plane of depth / sparse / gradients this tile works on
     const bool has_left = ccx > 0, has_right = ccx < p.cx - 1, has_up = ccy > 0, has_down = ccy < p.cy - 1;
     const int H = p.H, W = p.W;
     const size_t hw = (size_t)H * W;
@@ -314,7 +316,7 @@ __device__ __forceinline__ void fused_tile(const FusedParams<T>& p, const CUtens
     TRACE(1);
     const bool hw_cluster = multi && !GLB;
 
-    const T* db = p.depth + (size_t)plane * hw;
+    const T* db = p.depth + dplane * hw;
     const T* sb = p.sparse ? p.sparse + ((size_t)b * p.sparse_channels + (p.sparse_channels == 1 ? 0 : ch)) * hw : nullptr;
 
     // ---- prologue: loop-invariant weights n'_j = (1-m) * n_j, re-injection c = m*d0, r^0 = d0 -------------
@@ -888,7 +890,7 @@ __device__ __forceinline__ void fused_tile(const FusedParams<T>& p, const CUtens
             for (int j = 0; j < 8; ++j) gn[i][j] = 0ull;
         }
         {   // G^T = dL/d out on the whole tile (zero outside the image)
-            const T* gob = p.gout + (size_t)plane * hw;
+            const T* gob = p.gout + dplane * hw;
             if (vec_ok) {
                 typedef typename std::conditional<sizeof(T) == 4, float2, __half2>::type V2;
                 const int cgx = min(max(gx, 0), W - 2);
@@ -1005,7 +1007,7 @@ __device__ __forceinline__ void fused_tile(const FusedParams<T>& p, const CUtens
         // 1/S and the sign of the raw guidance come from the stash the prologue left in shared memory.
         // Mode OURS reads its 8 guidance values again to redo the softmax (the forward zeroed border taps).
         T* ggb = p.gg + (size_t)b * p.Cg * hw;
-        T* gdb = p.gd + (size_t)plane * hw;
+        T* gdb = p.gd + dplane * hw;
         const float qnan = __int_as_float(0x7fc00000);
         const u64 qnan2 = pk(qnan, qnan), one2 = pk(1.f, 1.f), mone2 = pk(-1.f, -1.f);
         if (lane_auth) {

@@ -399,3 +399,38 @@ def test_two_gpu_threaded_replicas():
         assert results[i] is not None
         assert torch.equal(results[i][0], y_full.detach().cpu()[sl])
         assert torch.equal(results[i][1], tg_full.grad.cpu()[sl]) and torch.equal(results[i][2], td_full.grad.cpu()[sl])
+
+
+def test_fused_backward_with_several_depth_channels():
+    """C > 1 depth channels share the affinity of their image (pac.py:77-78,118-119): the fused backward runs once per
+    channel and accumulates grad_guidance - C + (C - 1) launches instead of the generic path's ~50 - for both modes, one /
+    C sparse channels, fp32 and fp16."""
+    for mode, cg, c, sc, dtype in ((0, 12, 3, 1, torch.float32), (1, 8, 2, 2, torch.float32), (0, 8, 3, 3, torch.float16)):
+        g, d, s = make_inputs(33 + c + mode, 2, cg, c, 120, 136, density=0.04, sparse_channels=sc)
+        go = np.random.default_rng(c).standard_normal(d.shape).astype(np.float32)
+        if dtype == torch.float16:
+            g, d, s, go = (a.astype(np.float16).astype(np.float32) for a in (g, d, s, go))
+        y, tg, td = _run(mode, g, d, s, 24, requires_grad=True, dtype=dtype)
+        y.backward(_cu(go, dtype))
+        # launch count through the raw C ABI on this thread (autograd runs the module's backward on its own thread, and the
+        # library's call statistics are per host thread)
+        lib = _lib.load()
+        b, _, h, w = d.shape
+        n = lib.cspn_bwd_workspace_bytes(b, c, h, w, 24, 3, mode)
+        ws = torch.empty(n, dtype=torch.uint8, device=DEV)
+        raw = [_cu(a, dtype) for a in (go, g, d, s)]
+        gg_raw, gd_raw = torch.empty_like(raw[1]), torch.empty_like(raw[2])
+        fn = lib.cspn_bwd_f32 if dtype == torch.float32 else lib.cspn_bwd_f16
+        rc = fn(raw[0].data_ptr(), raw[1].data_ptr(), cg * h * w, cg, raw[2].data_ptr(), raw[3].data_ptr(), sc, gg_raw.data_ptr(), gd_raw.data_ptr(),
+                b, c, h, w, 24, 3, mode, ws.data_ptr(), n, torch.cuda.current_stream().cuda_stream)
+        assert rc == 0 and lib.cspn_last_path() == _lib.PATH_FUSED and lib.cspn_last_launch_count() == 2 * c - 1
+        torch.cuda.synchronize()
+        assert torch.equal(gg_raw, tg.grad) and torch.equal(gd_raw, td.grad)
+        gg, gd = c_oracle.backward(g, d, s, go, 24, 3, mode, threads=0)
+        ulp = 2.0 ** -10 if dtype == torch.float16 else 0.0
+        for got, want, what in ((td.grad, gd, "grad_depth"), (tg.grad, gg, "grad_guidance")):
+            e = np.abs(got.float().cpu().numpy() - want)
+            tol = np.abs(want) * ulp * c + GRAD_RTOL * max(1.0, np.abs(want).max())
+            assert (e <= tol).all(), f"C={c} mode {mode} {dtype} {what}: max err {e.max():.3e}"
+        if cg > 8:
+            assert torch.count_nonzero(tg.grad[:, 8:]) == 0
