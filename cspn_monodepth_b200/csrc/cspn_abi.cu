@@ -300,9 +300,9 @@ int forward_host_submit_impl(const T* guidance, int64_t gbs, const T* depth, con
     T* dout = (T*)q; q += up(d_bytes);
     T* ds = sparse ? (T*)q : nullptr; q += up(s_bytes);
     void* dws = (void*)q;
-    // the dual-slot kernel reports an exchange timeout through the first int of its workspace (device buffers are aligned,
-    // so a dual-slot plan is what runs); other kernels have no such word
-    const bool has_status = iters > 0 && use_fused(B, C, H, W, iters, ksize, mode, nullptr) && dual_supported(B, C, H, W, iters, ksize, mode);
+    // fused plans that exchange halos through global memory (stream mode, dual-slot kernel) report a timeout through the
+    // first int of their workspace; hardware-cluster plans need no workspace and cannot time out
+    const bool has_status = iters > 0 && use_fused(B, C, H, W, iters, ksize, mode, nullptr) && fused_workspace(B, C, H, W, iters, ksize, mode) > 0;
     *sl.status_host = 0;
     cudaError_t e = cudaSuccess;
     {

@@ -42,7 +42,7 @@ static size_t single_workspace(int B, int C, int H, int W, int iters)
     if (!single_ok(B, C, H, W, iters)) return 0;
     const Tiling tl = plan_forward(B, C, H, W, iters);
     if (!tl.stream) return 0;
-    return (size_t)(tl.ctas * (long)B * C) * inbox_bytes<kTHBig>();     // inboxes of the global-memory exchange, one per tile
+    return kStatusBytes + (size_t)(tl.ctas * (long)B * C) * inbox_bytes<kTHBig>();     // status word + inboxes of the global-memory exchange, one per tile
 }
 
 // Sized for whichever kernel the launch ends up with: the dual-slot kernel can still hand over to the single-tile one

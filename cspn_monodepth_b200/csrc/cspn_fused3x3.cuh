@@ -201,6 +201,7 @@ struct FusedParams {
     uint32_t total_tiles; // GLB exchange only: cx * cy * planes tiles, processed by a persistent grid
     uint4* inbox;         // GLB exchange only: one Inbox per CTA tile in global memory
     uint32_t tag_base;    // GLB exchange only: tag of refresh e is tag_base + e
+    int* status;          // GLB exchange only: set to 1 when a neighbour never showed up (the results are NaN-filled as well)
     // backward only
     const T* gout;        // dL/d out
     T* gg; T* gd;         // dL/d guidance [B, Cg, H, W], dL/d depth [B, 1, H, W]
@@ -1105,6 +1106,7 @@ __device__ __forceinline__ void fused_tile(const FusedParams<T>& p, const CUtens
             }
         }
     }
+    if (GLB && poisoned && p.status && lane == 0) *p.status = 1;
     TRACE(15);
 }
 
@@ -1129,6 +1131,7 @@ fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant_
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    if (GLB && blockIdx.x == 0 && threadIdx.x == 0 && p.status) *p.status = 0;     // a timeout (2^21 polls later at the earliest) sets it to 1
     if (!GLB) {
         // "my barriers exist": neighbours may only push into this CTA after everyone passed the matching wait
         if (p.cx * p.cy > 1) cluster_arrive();
@@ -1280,6 +1283,7 @@ bool make_guidance_map(const T* guidance, int64_t gbs, int B, int H, int W, CUte
 }
 
 template <int TH> constexpr size_t inbox_bytes() { return (size_t)InboxGeom<TH>::size * sizeof(uint4); }
+constexpr size_t kStatusBytes = 256;     // stream-mode scratch starts with the status word (rest of the 256 bytes unused)
 
 template <typename T, int P, int NW, int MODE, bool TMA, bool BWD>
 constexpr size_t fused_smem_bytes()
@@ -1297,9 +1301,18 @@ int launch_variant(const FusedParams<T>& p, const CUtensorMap& map, const Tiling
     auto kern = fused3x3_kernel<T, P, NW, MODE, TMA, GLB, BWD>;
     constexpr size_t smem = fused_smem_bytes<T, P, NW, MODE, TMA, BWD>();
     static_assert(smem * (NW <= 5 ? 2 : 1) <= 227 * 1024, "shared memory budget of one SM exceeded");
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // the two opt-ins are per device and last for the life of the context: set them once per device, not on every launch
+    static std::atomic<uint64_t> configured{0};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return (int)e;
+    const uint64_t bit = 1ull << (dev & 63);
+    if (!(configured.load(std::memory_order_acquire) & bit)) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        configured.fetch_or(bit, std::memory_order_release);
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = GLB ? dim3((unsigned)grid_ctas) : dim3((unsigned)(tl.ntx * tl.cx), (unsigned)(tl.nty * tl.cy), (unsigned)planes);
     cfg.blockDim = dim3(NW * 32);
@@ -1391,7 +1404,9 @@ int launch(FusedParams<T> p, const Tiling& tl, int B, void* inbox, size_t inbox_
     long grid_ctas = 0;
     if (glb) {
         const long total = tl.ctas * planes;
-        if (!inbox || inbox_avail < (size_t)total * inbox_bytes<TH>()) return CSPN_ERR_WORKSPACE;
+        if (!inbox || inbox_avail < kStatusBytes + (size_t)total * inbox_bytes<TH>()) return CSPN_ERR_WORKSPACE;
+        p.status = (int*)inbox;                                       // first word of the scratch: exchange-timeout flag
+        inbox = (char*)inbox + kStatusBytes;
         const Capacity cap = capacity<P, NW, BWD>();
         grid_ctas = total < cap.sms ? total : cap.sms;
         p.total_tiles = (uint32_t)total;

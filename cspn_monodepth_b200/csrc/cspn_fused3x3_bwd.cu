@@ -28,7 +28,7 @@ inline size_t gg_scratch_bytes(int B, int C, int H, int W) { return C > 1 ? up25
 inline size_t bwd_inbox_bytes(const Tiling& tl, int B)
 {
     if (!tl.stream) return 0;
-    return up256((size_t)(tl.ctas * (long)B) * inbox_bytes<kTHBwd>());
+    return up256(kStatusBytes + (size_t)(tl.ctas * (long)B) * inbox_bytes<kTHBwd>());     // status word + one inbox per tile
 }
 }  // namespace
 

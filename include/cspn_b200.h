@@ -74,7 +74,8 @@ extern "C" {
 #define CSPN_ERR_ALIAS (-8)          /* out aliases an input */
 #define CSPN_ERR_EXCHANGE_TIMEOUT (-9) /* host entry points only: a tile of a fused kernel never received its neighbours' halo ring
                                           (bounded spin expired; the output is NaN-filled).  Device entry points are asynchronous:
-                                          a CSPN_KERNEL_DUAL forward (cspn_fwd_plan) reports it through the first int of
+                                          a fused forward / backward whose plan exchanges halos through global memory (any fused
+                                          3x3 call with a non-zero cspn_*_workspace_bytes) reports it through the first int of
                                           `workspace` (0 = fine, 1 = timeout), valid once the stream has reached the end of the call. */
 
 /* path selection (cspn_set_path): which CUDA implementation the forward uses */

@@ -87,7 +87,7 @@ def test_planner_picks_kernel_and_workspace_by_problem_size():
     assert _lib.forward_plan(8, 1, 228, 304, 24)["kernel"] == _lib.KERNEL_SINGLE
     assert lib.cspn_fwd_workspace_bytes(1, 1, 228, 304, 24, 3, 0) == 0                 # one 5x3 cluster: DSMEM
     assert lib.cspn_fwd_workspace_bytes(7, 1, 228, 304, 24, 3, 0) == 0                 # 7 clusters of 15 fit at once
-    assert lib.cspn_fwd_workspace_bytes(8, 1, 228, 304, 24, 3, 0) == 8 * 15 * inbox    # the 8th would not: stream mode, 120 tiles
+    assert lib.cspn_fwd_workspace_bytes(8, 1, 228, 304, 24, 3, 0) == 256 + 8 * 15 * inbox    # the 8th would not: stream mode, status word + 120 inboxes
     assert lib.cspn_fwd_workspace_bytes(32, 1, 352, 1216, 24, 3, 0) == 0               # KITTI batch: 4x2 hardware clusters
     assert lib.cspn_fwd_workspace_bytes(8, 1, 64, 64, 24, 3, 0) == 0                   # single-tile images
     # one image with more tiles than SMs (720p: 22 x 10 = 220): never the lockstep stream (it would wait on tiles that have
@@ -102,7 +102,7 @@ def test_planner_picks_kernel_and_workspace_by_problem_size():
     hist = 192 * 24 * 64 * 64 * 4
     assert lib.cspn_bwd_workspace_bytes(1, 1, 60, 60, 24, 3, 0) == hist                # one tile: history only
     n = lib.cspn_bwd_workspace_bytes(8, 1, 228, 304, 24, 3, 0)
-    assert n == hist + 8 * 20 * (4 * 64 + 4 * 2 * 32) * 16                             # stream mode: 20 tiles of 64x64 per image
+    assert n == hist + 256 + 8 * 20 * (4 * 64 + 4 * 2 * 32) * 16                       # stream mode: status word + 20 tiles of 64x64 per image
 
 
 def test_dual_slot_planner_is_opt_in():
@@ -138,3 +138,15 @@ def test_torch_library_layer_registers_the_operators():
         torch.ops.cspn.forward(g, d, None, 2, 3, 0)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         torch.ops.cspn.backward(d, g, d, None, 2, 3, 0)
+
+
+def test_pipelined_host_api_argument_validation_without_gpu():
+    lib = _lib.load()
+    one = ctypes.c_float(0.0)
+    p = ctypes.addressof(one)
+    t = ctypes.c_int(7)
+    assert lib.cspn_fwd_host_submit_f32(p, 8 * 16, p, None, 1, p, 1, 1, 4, 4, 2, 3, 9, ctypes.byref(t)) == -4 and t.value == 0
+    assert lib.cspn_fwd_host_submit_f32(p, 8 * 16, p, None, 1, p, 0, 1, 4, 4, 2, 3, 0, ctypes.byref(t)) == 0 and t.value == 0     # empty batch: no ticket
+    assert lib.cspn_fwd_host_submit_f32(p, 8 * 16, p, None, 1, p, 1, 1, 4, 4, 2, 3, 0, None) == -1
+    assert lib.cspn_host_wait(0) == 0 and lib.cspn_host_pipeline_depth() >= 2
+    assert lib.cspn_error_string(-9).startswith(b"cspn:")

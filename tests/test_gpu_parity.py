@@ -434,3 +434,42 @@ def test_fused_backward_with_several_depth_channels():
             assert (e <= tol).all(), f"C={c} mode {mode} {dtype} {what}: max err {e.max():.3e}"
         if cg > 8:
             assert torch.count_nonzero(tg.grad[:, 8:]) == 0
+
+
+def test_pipelined_host_entry_points():
+    """cspn_fwd_host_submit_* / cspn_host_wait: several calls in flight (H2D of one overlaps kernel + D2H of the previous),
+    every result checked against the oracle; fp32 with a strided 12-channel guidance and fp16; tickets are per call."""
+    lib = _lib.load()
+    depth = lib.cspn_host_pipeline_depth()
+    assert depth >= 2
+    cases = []
+    for i in range(2 * depth + 1):
+        g, d, s = make_inputs(200 + i, 8 if i % 2 == 0 else 3, 12, 1, 228, 304, density=0.0072)
+        cases.append((g, d, s))
+    pinned = [[torch.from_numpy(a).pin_memory() for a in c] for c in cases]
+    outs = [torch.empty_like(p[1]).pin_memory() for p in pinned]
+    tickets = []
+    for (hg, hd, hs), out in zip(pinned, outs):
+        t = ctypes.c_int(0)
+        b = hd.shape[0]
+        rc = lib.cspn_fwd_host_submit_f32(hg.data_ptr(), 12 * 228 * 304, hd.data_ptr(), hs.data_ptr(), 1, out.data_ptr(), b, 1, 228, 304, 24, 3, 0, ctypes.byref(t))
+        assert rc == 0 and t.value > 0
+        tickets.append(t.value)
+    assert len(set(tickets)) == len(tickets)
+    for t in reversed(tickets):                      # waiting out of order is fine (older calls were retired by later submits)
+        assert lib.cspn_host_wait(t) == 0
+    assert lib.cspn_host_wait(tickets[0]) == 0      # waiting twice is a no-op
+    for (g, d, s), out in zip(cases, outs):
+        assert_close_nan(out.numpy(), c_oracle.forward(g, d, s, 24, 3, 0, threads=0), FWD_ATOL, "pipelined host entry")
+    g, d, s = (a.astype(np.float16) for a in make_inputs(300, 2, 8, 1, 352, 1216, density=0.05))
+    hg, hd, hs = (torch.from_numpy(a).pin_memory() for a in (g, d, s))
+    out = torch.empty_like(hd).pin_memory()
+    t = ctypes.c_int(0)
+    assert lib.cspn_fwd_host_submit_f16(hg.data_ptr(), 8 * 352 * 1216, hd.data_ptr(), hs.data_ptr(), 1, out.data_ptr(), 2, 1, 352, 1216, 24, 3, 0, ctypes.byref(t)) == 0
+    assert lib.cspn_host_wait(t.value) == 0
+    ref = c_oracle.forward(g.astype(np.float32), d.astype(np.float32), s.astype(np.float32), 24, 3, 0, threads=0)
+    err = np.abs(out.float().numpy() - ref)
+    assert (err <= np.abs(ref) * 2.0 ** -10 + FWD_ATOL).all()
+    t0 = ctypes.c_int(5)
+    assert lib.cspn_fwd_host_submit_f32(hg.data_ptr(), 8, hd.data_ptr(), None, 1, out.data_ptr(), 0, 1, 4, 4, 2, 3, 0, ctypes.byref(t0)) == 0 and t0.value == 0   # empty batch
+    assert lib.cspn_fwd_host_submit_f32(None, 8 * 16, hd.data_ptr(), None, 1, out.data_ptr(), 1, 1, 4, 4, 2, 3, 0, ctypes.byref(t0)) == -1
