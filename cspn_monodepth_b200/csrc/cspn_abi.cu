@@ -428,6 +428,44 @@ int cspn_fwd_host_f32(const float* guidance, int64_t gbs, const float* depth, co
 {
     return forward_host_impl<float>(guidance, gbs, depth, sparse, sparse_channels, out, B, C, H, W, iters, ksize, mode, stream);
 }
+size_t cspn_loss_workspace_bytes(void) { return loss_workspace_bytes(); }
+int cspn_masked_l1_fwd_f32(const float* pred, const float* target, int64_t n, float* loss2, void* ws, size_t ws_bytes, void* stream)
+{
+    if (n < 0) return CSPN_ERR_BAD_SHAPE;
+    call_stats().launches = 0;
+    return masked_l1_forward<float>(pred, target, (size_t)n, loss2, ws, ws_bytes, (cudaStream_t)stream);
+}
+int cspn_masked_l1_fwd_f16(const void* pred, const void* target, int64_t n, float* loss2, void* ws, size_t ws_bytes, void* stream)
+{
+    if (n < 0) return CSPN_ERR_BAD_SHAPE;
+    call_stats().launches = 0;
+    return masked_l1_forward<__half>((const __half*)pred, (const __half*)target, (size_t)n, loss2, ws, ws_bytes, (cudaStream_t)stream);
+}
+int cspn_masked_l1_bwd_f32(const float* pred, const float* target, int64_t n, const float* loss2, const float* grad_loss, float* grad_pred, void* stream)
+{
+    if (n < 0) return CSPN_ERR_BAD_SHAPE;
+    call_stats().launches = 0;
+    return masked_l1_backward<float>(pred, target, (size_t)n, loss2, grad_loss, grad_pred, (cudaStream_t)stream);
+}
+int cspn_masked_l1_bwd_f16(const void* pred, const void* target, int64_t n, const float* loss2, const float* grad_loss, void* grad_pred, void* stream)
+{
+    if (n < 0) return CSPN_ERR_BAD_SHAPE;
+    call_stats().launches = 0;
+    return masked_l1_backward<__half>((const __half*)pred, (const __half*)target, (size_t)n, loss2, grad_loss, (__half*)grad_pred, (cudaStream_t)stream);
+}
+int cspn_depth_metrics_f32(const float* pred, const float* target, int64_t n, float* out11, void* ws, size_t ws_bytes, void* stream)
+{
+    if (n < 0) return CSPN_ERR_BAD_SHAPE;
+    call_stats().launches = 0;
+    return depth_metrics<float>(pred, target, (size_t)n, out11, ws, ws_bytes, (cudaStream_t)stream);
+}
+int cspn_depth_metrics_f16(const void* pred, const void* target, int64_t n, float* out11, void* ws, size_t ws_bytes, void* stream)
+{
+    if (n < 0) return CSPN_ERR_BAD_SHAPE;
+    call_stats().launches = 0;
+    return depth_metrics<__half>((const __half*)pred, (const __half*)target, (size_t)n, out11, ws, ws_bytes, (cudaStream_t)stream);
+}
+
 int cspn_fwd_host_submit_f32(const float* guidance, int64_t gbs, const float* depth, const float* sparse, int sparse_channels,
                              float* out, int B, int C, int H, int W, int iters, int ksize, int mode, int* ticket)
 {

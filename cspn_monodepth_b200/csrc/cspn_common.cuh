@@ -111,4 +111,10 @@ bool fused_bwd_supported(int C, int H, int W, int iters, int ksize, int mode);
 template <typename T> int fused_backward(const BwdArgs<T>& a);
 size_t fused_bwd_workspace(int B, int C, int H, int W, int iters);
 
+// loss / metrics downstream of the module (cspn_loss.cu): one deterministic streaming pass each
+size_t loss_workspace_bytes();
+template <typename T> int masked_l1_forward(const T* pred, const T* target, size_t n, float* loss2, void* ws, size_t ws_bytes, cudaStream_t stream);
+template <typename T> int masked_l1_backward(const T* pred, const T* target, size_t n, const float* loss2, const float* grad_loss, T* grad_pred, cudaStream_t stream);
+template <typename T> int depth_metrics(const T* pred, const T* target, size_t n, float* out11, void* ws, size_t ws_bytes, cudaStream_t stream);
+
 }  // namespace cspn

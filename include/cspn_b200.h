@@ -155,6 +155,24 @@ CSPN_API int cspn_fwd_host_submit_f16(const void* guidance, int64_t guidance_bat
 CSPN_API int cspn_host_wait(int ticket);
 CSPN_API int cspn_host_pipeline_depth(void);
 
+/* ---- directly downstream of the module -----------------------------------------------------------
+ * Masked L1 loss, libs/criterion/criteria.py:27-39 (MaskedL1Loss; reached through Criterion_No_DSN :170-188):
+ *   loss = mean |target - pred| over the n elements with target > 0 (NaN when there is none, like the reference's mean of an
+ *   empty tensor).  One streaming pass, deterministic two-stage reduction (no floating-point atomics).
+ *   loss2 (device, 2 floats) = {loss, number of valid elements}; the backward reads it back:
+ *   grad_pred[i] = grad_loss[0] * -sign(target[i] - pred[i]) / count on valid elements, 0 elsewhere (grad_loss NULL = 1).
+ * Depth metrics, libs/metrics.py:49-83 (Result.evaluate), same pass structure:
+ *   out11 (device, 11 floats) = {irmse, imae, mse, rmse, mae, absrel, lg10, delta1, delta2, delta3, valid count}.
+ * workspace: cspn_loss_workspace_bytes() bytes, 8-byte aligned, ZEROED ONCE before its first use (the kernels leave it ready
+ * for the next call); pred / target are device pointers, fp32 or fp16 (accumulation in double). */
+CSPN_API size_t cspn_loss_workspace_bytes(void);
+CSPN_API int cspn_masked_l1_fwd_f32(const float* pred, const float* target, int64_t n, float* loss2, void* workspace, size_t workspace_bytes, void* stream);
+CSPN_API int cspn_masked_l1_fwd_f16(const void* pred, const void* target, int64_t n, float* loss2, void* workspace, size_t workspace_bytes, void* stream);
+CSPN_API int cspn_masked_l1_bwd_f32(const float* pred, const float* target, int64_t n, const float* loss2, const float* grad_loss, float* grad_pred, void* stream);
+CSPN_API int cspn_masked_l1_bwd_f16(const void* pred, const void* target, int64_t n, const float* loss2, const float* grad_loss, void* grad_pred, void* stream);
+CSPN_API int cspn_depth_metrics_f32(const float* pred, const float* target, int64_t n, float* out11, void* workspace, size_t workspace_bytes, void* stream);
+CSPN_API int cspn_depth_metrics_f16(const void* pred, const void* target, int64_t n, float* out11, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
