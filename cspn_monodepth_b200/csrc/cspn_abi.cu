@@ -125,6 +125,24 @@ int backward_impl(const T* grad_out, const T* guidance, int64_t gbs, int Cg, con
     return rc;
 }
 
+template <typename T>
+int legacy_impl(const T* guidance, int64_t gbs, const T* depth, const T* sparse, T* out, int B, int H, int W, int iters, void* ws, size_t ws_bytes,
+                void* stream)
+{
+    if (B < 0 || H < 1 || W < 1 || iters < 1) return CSPN_ERR_BAD_SHAPE;
+    if ((uint64_t)B * (uint64_t)H * (uint64_t)W > (1ull << 40)) return CSPN_ERR_BAD_SHAPE;
+    if (B == 0) return CSPN_OK;
+    if (!guidance || !depth || !out) return CSPN_ERR_NULL_POINTER;
+    const size_t hw = (size_t)H * W, nout = (size_t)B * hw * sizeof(T);
+    if (gbs < (int64_t)8 * (int64_t)hw) return CSPN_ERR_BAD_STRIDE;
+    if (overlaps(out, nout, depth, nout) || overlaps(out, nout, guidance, (size_t)B * gbs * sizeof(T)) || (sparse && overlaps(out, nout, sparse, nout)))
+        return CSPN_ERR_ALIAS;
+    call_stats().launches = 0;
+    const int rc = legacy_forward<T>(guidance, gbs, depth, sparse, out, B, H, W, iters, ws, ws_bytes, (cudaStream_t)stream);
+    if (rc == CSPN_OK) call_stats().path = CSPN_PATH_BLOCKED;
+    return rc;
+}
+
 // Per host thread and device state of the host entry points, created once:
 //  * a private stream-ordered memory pool that KEEPS its memory (release threshold = max): with the default pool every
 //    cudaStreamSynchronize hands the scratch back to the driver and the next call pays a fresh allocation (~0.3 ms);
@@ -427,6 +445,21 @@ int cspn_fwd_host_f32(const float* guidance, int64_t gbs, const float* depth, co
                       float* out, int B, int C, int H, int W, int iters, int ksize, int mode, void* stream)
 {
     return forward_host_impl<float>(guidance, gbs, depth, sparse, sparse_channels, out, B, C, H, W, iters, ksize, mode, stream);
+}
+size_t cspn_legacy_workspace_bytes(int B, int H, int W, int iters)
+{
+    if (B < 1 || H < 1 || W < 1 || iters < 1) return 0;
+    return legacy_workspace(B, H, W, iters);
+}
+int cspn_legacy_fwd_f32(const float* guidance, int64_t gbs, const float* depth, const float* sparse, float* out, int B, int H, int W, int iters,
+                        void* ws, size_t ws_bytes, void* stream)
+{
+    return legacy_impl<float>(guidance, gbs, depth, sparse, out, B, H, W, iters, ws, ws_bytes, stream);
+}
+int cspn_legacy_fwd_f16(const void* guidance, int64_t gbs, const void* depth, const void* sparse, void* out, int B, int H, int W, int iters,
+                        void* ws, size_t ws_bytes, void* stream)
+{
+    return legacy_impl<__half>((const __half*)guidance, gbs, (const __half*)depth, (const __half*)sparse, (__half*)out, B, H, W, iters, ws, ws_bytes, stream);
 }
 size_t cspn_loss_workspace_bytes(void) { return loss_workspace_bytes(); }
 int cspn_masked_l1_fwd_f32(const float* pred, const float* target, int64_t n, float* loss2, void* ws, size_t ws_bytes, void* stream)

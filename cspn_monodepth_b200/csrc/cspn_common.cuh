@@ -111,6 +111,11 @@ bool fused_bwd_supported(int C, int H, int W, int iters, int ksize, int mode);
 template <typename T> int fused_backward(const BwdArgs<T>& a);
 size_t fused_bwd_workspace(int B, int C, int H, int W, int iters);
 
+// legacy max-of-8 CSPN (cspn_legacy.cu): temporally blocked forward, 4 steps per launch
+size_t legacy_workspace(int B, int H, int W, int iters);
+template <typename T> int legacy_forward(const T* guidance, int64_t gbs, const T* depth, const T* sparse, T* out, int B, int H, int W, int iters,
+                                         void* ws, size_t ws_bytes, cudaStream_t stream);
+
 // loss / metrics downstream of the module (cspn_loss.cu): one deterministic streaming pass each
 size_t loss_workspace_bytes();
 template <typename T> int masked_l1_forward(const T* pred, const T* target, size_t n, float* loss2, void* ws, size_t ws_bytes, cudaStream_t stream);

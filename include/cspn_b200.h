@@ -155,6 +155,20 @@ CSPN_API int cspn_fwd_host_submit_f16(const void* guidance, int64_t guidance_bat
 CSPN_API int cspn_host_wait(int ticket);
 CSPN_API int cspn_host_pipeline_depth(void);
 
+/* ---- legacy max-of-8 CSPN ---------------------------------------------------------------------------
+ * network/libs/post_process/CSPN.py:19-56, AffinityPropagate().forward(guidance, blur_depth, sparse_depth), and :132-164,
+ * AffinityPropagate_prediction().forward(guidance, blur_depth) (sparse == NULL).  Per step and gate k = 0..7 (|guidance[:,k]|,
+ * not shifted): out_k = box3x3(g_k * r) / box3x3(g_k) (zero padded, centre included), r = max_k out_k (NaN propagates like
+ * torch.max), r = (1 - m) r + m * sparse with m = sign(sparse): the SPARSE SAMPLE is re-injected and also seeds r^0.  The
+ * reference runs a fixed 16 steps (:35); `iters` >= 1 is a parameter here.  One depth channel, one sparse channel; guidance
+ * may carry more than 8 channels (batch stride in elements).  Forward only: 4 steps per launch, ceil(iters / 4) launches
+ * (cspn_legacy.cu); workspace = cspn_legacy_workspace_bytes, 16-byte aligned.  Same conventions as cspn_fwd_*. */
+CSPN_API size_t cspn_legacy_workspace_bytes(int B, int H, int W, int iters);
+CSPN_API int cspn_legacy_fwd_f32(const float* guidance, int64_t guidance_batch_stride, const float* depth, const float* sparse, float* out,
+                                 int B, int H, int W, int iters, void* workspace, size_t workspace_bytes, void* stream);
+CSPN_API int cspn_legacy_fwd_f16(const void* guidance, int64_t guidance_batch_stride, const void* depth, const void* sparse, void* out,
+                                 int B, int H, int W, int iters, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- directly downstream of the module -----------------------------------------------------------
  * Masked L1 loss, libs/criterion/criteria.py:27-39 (MaskedL1Loss; reached through Criterion_No_DSN :170-188):
  *   loss = mean |target - pred| over the n elements with target > 0 (NaN when there is none, like the reference's mean of an
