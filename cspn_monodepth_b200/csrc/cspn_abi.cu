@@ -51,6 +51,11 @@ bool use_blocked(int B, int C, int H, int W, int iters, int ksize, int mode)
     return g_path.load(std::memory_order_relaxed) == CSPN_PATH_AUTO && blocked5x5_supported(B, C, H, W, iters, ksize, mode);
 }
 
+bool use_blocked_bwd(int B, int C, int H, int W, int iters, int ksize, int mode)
+{
+    return g_path.load(std::memory_order_relaxed) == CSPN_PATH_AUTO && blocked5x5_bwd_supported(B, C, H, W, iters, ksize, mode);
+}
+
 bool use_fused_bwd(int C, int H, int W, int iters, int ksize, int mode, int* err)
 {
     const int path = g_path.load(std::memory_order_relaxed);
@@ -116,6 +121,11 @@ int backward_impl(const T* grad_out, const T* guidance, int64_t gbs, int Cg, con
         return rc;
     }
     if (err != CSPN_OK) return err;
+    if (iters > 0 && use_blocked_bwd(B, C, H, W, iters, ksize, mode)) {
+        rc = blocked5x5_backward<T>(a);
+        if (rc == CSPN_OK) call_stats().path = CSPN_PATH_BLOCKED;
+        return rc;
+    }
     if (iters > 0) {
         const size_t need = generic_bwd_workspace(B, C, H, W, iters, tt.n);
         if (!ws || ws_bytes < need) return CSPN_ERR_WORKSPACE;
@@ -412,6 +422,7 @@ size_t cspn_bwd_workspace_bytes(int B, int C, int H, int W, int iters, int ksize
     TapTable tt;
     if (!make_taps(mode, ksize, &tt) || B < 1 || C < 1 || H < 1 || W < 1 || iters < 1) return 0;
     if (use_fused_bwd(C, H, W, iters, ksize, mode, nullptr)) return fused_bwd_workspace(B, C, H, W, iters);
+    if (use_blocked_bwd(B, C, H, W, iters, ksize, mode)) return blocked5x5_bwd_workspace(B, C, H, W, iters);
     return generic_bwd_workspace(B, C, H, W, iters, tt.n);
 }
 

@@ -63,10 +63,17 @@ __device__ __forceinline__ void load_quad(const TP* plane, int gy, int gx, int H
         if (gx + q >= 0 && gx + q < W) o[q] = to_f32(row[gx + q]);
 }
 
-template <typename T, typename TIn, typename TOut>
+// REV = false: the forward recurrence.  REV = true: the adjoint recurrence of the backward pass,
+//   G^t(q) = sum_j k'_j(q - o_j) G^{t+1}(q - o_j),  k' = (1 - m) softmax  (pac.py:96-121 through the loop of CSPN_ours.py:47-53),
+// which is the SAME 24-tap gather once every thread holds the transposed weights wt_j(q) = k'_j(q - o_j): they are fetched from
+// the neighbours through shared memory once per launch (12 rounds of 2 tap planes), then the S steps run exactly like the forward.
+// hist != nullptr: the exact inner block of every step's result (the first hist_count steps) also goes to the fp32 plane set
+// hist + s * hist_step - the backward pass needs every r^t and every G^t.  rout may then be nullptr.
+template <typename T, typename TIn, typename TOut, bool REV>
 __global__ void __launch_bounds__(kThreads, 1)
 blocked5x5_kernel(const T* __restrict__ g, int64_t gbs, const TIn* __restrict__ rin, const T* __restrict__ d0,
                   const T* __restrict__ sparse, int sparse_channels, TOut* __restrict__ rout,
+                  float* __restrict__ hist, long long hist_step, int hist_count,
                   int C, int H, int W, int steps, int vec)
 {
     __shared__ __align__(16) float buf[2][kSH][kSW];
@@ -94,7 +101,8 @@ blocked5x5_kernel(const T* __restrict__ g, int64_t gbs, const TIn* __restrict__ 
         }
     }
     float dq[4], mq[4], rq[4];
-    load_quad(d0 + (size_t)plane * hw, gy, gx, H, W, vec != 0, dq);
+    dq[0] = dq[1] = dq[2] = dq[3] = 0.f;
+    if (!REV) load_quad(d0 + (size_t)plane * hw, gy, gx, H, W, vec != 0, dq);
     load_quad(rin + (size_t)plane * hw, gy, gx, H, W, vec != 0, rq);
     mq[0] = mq[1] = mq[2] = mq[3] = 0.f;
     if (sparse) {
@@ -116,9 +124,28 @@ blocked5x5_kernel(const T* __restrict__ g, int64_t gbs, const TIn* __restrict__ 
         const float f = in ? (1.f - mq[q]) / s : 0.f;
 #pragma unroll
         for (int j = 0; j < 24; ++j) w[q][j] *= f;
-        cq[q] = in ? mq[q] * dq[q] : 0.f;
+        cq[q] = (in && !REV) ? mq[q] * dq[q] : 0.f;
     }
     __syncthreads();                                                                    // zero fill done
+    if (REV) {
+        // transposed weights: tap j of pixel q is the weight pixel q - o_j applies to ITS tap j.  Pixels whose source lies
+        // outside the region read the zero frame - they are within 2 pixels of the region edge, never part of an exact result.
+#pragma unroll
+        for (int r = 0; r < 12; ++r) {
+            // taps r and 23 - r have opposite offsets (o_{23-r} = -o_r): in gather form the tap with offset o_r must carry
+            // k'_{23-r}(q + o_r), the tap with offset -o_r carries k'_r(q - o_r)
+            *reinterpret_cast<float4*>(&buf[0][ry + kPadY][kPadX + qx * kQuad]) = make_float4(w[0][r], w[1][r], w[2][r], w[3][r]);
+            *reinterpret_cast<float4*>(&buf[1][ry + kPadY][kPadX + qx * kQuad]) = make_float4(w[0][23 - r], w[1][23 - r], w[2][23 - r], w[3][23 - r]);
+            __syncthreads();
+            const int dy = r / 5 - 2, dx = r % 5 - 2;
+#pragma unroll
+            for (int q = 0; q < kQuad; ++q) {
+                w[q][23 - r] = buf[0][ry + kPadY - dy][kPadX + qx * kQuad + q - dx];
+                w[q][r] = buf[1][ry + kPadY + dy][kPadX + qx * kQuad + q + dx];
+            }
+            __syncthreads();
+        }
+    }
     *reinterpret_cast<float4*>(&buf[0][ry + kPadY][kPadX + qx * kQuad]) = make_float4(rq[0], rq[1], rq[2], rq[3]);
     __syncthreads();
 
@@ -150,12 +177,22 @@ blocked5x5_kernel(const T* __restrict__ g, int64_t gbs, const TIn* __restrict__ 
         }
         }
         *reinterpret_cast<float4*>(&buf[(s + 1) & 1][ry + kPadY][kPadX + qx * kQuad]) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        if (hist != nullptr && s < hist_count && ry >= halo_y && ry < kRH - halo_y && qx * kQuad >= kHaloX && qx * kQuad < kRW - kHaloX && gy < H) {
+            float* hrow = hist + (long long)s * hist_step + (size_t)plane * hw + (size_t)gy * W;
+            if (vec) {
+                if (gx + 3 < W) *reinterpret_cast<float4*>(hrow + gx) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < kQuad; ++q)
+                    if (gx + q < W) hrow[gx + q] = acc[q];
+            }
+        }
         __syncthreads();
     }
 
     // ---- the exact inner block goes back to HBM
     const int lx = qx * kQuad;
-    if (ry >= halo_y && ry < kRH - halo_y && lx >= kHaloX && lx < kRW - kHaloX && gy < H) {
+    if (rout != nullptr && ry >= halo_y && ry < kRH - halo_y && lx >= kHaloX && lx < kRW - kHaloX && gy < H) {
         TOut* orow = rout + (size_t)plane * hw + (size_t)gy * W;
 #pragma unroll
         for (int q = 0; q < kQuad; ++q)
@@ -168,8 +205,8 @@ int launch_one(const FwdArgs<T>& a, const TIn* rin, TOut* rout, int steps, bool 
 {
     const int out_h = kRH - 4 * steps;
     dim3 grid((unsigned)((a.W + kOutW - 1) / kOutW), (unsigned)((a.H + out_h - 1) / out_h), (unsigned)(a.B * a.C));
-    blocked5x5_kernel<T, TIn, TOut><<<grid, kThreads, 0, a.stream>>>(a.guidance, a.gbs, rin, a.depth, a.sparse, a.sparse_channels, rout,
-                                                                      a.C, a.H, a.W, steps, vec ? 1 : 0);
+    blocked5x5_kernel<T, TIn, TOut, false><<<grid, kThreads, 0, a.stream>>>(a.guidance, a.gbs, rin, a.depth, a.sparse, a.sparse_channels, rout,
+                                                                             nullptr, 0, 0, a.C, a.H, a.W, steps, vec ? 1 : 0);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     ++call_stats().launches;
@@ -177,6 +214,159 @@ int launch_one(const FwdArgs<T>& a, const TIn* rin, TOut* rout, int steps, bool 
 }
 
 inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+__device__ __forceinline__ void store_quad(float* row, int gx, int W, bool vec, const float* v)
+{
+    if (vec) { if (gx + 3 < W) *reinterpret_cast<float4*>(row + gx) = make_float4(v[0], v[1], v[2], v[3]); return; }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (gx + q < W) row[gx + q] = v[q];
+}
+__device__ __forceinline__ void store_quad(__half* row, int gx, int W, bool vec, const float* v)
+{
+    if (vec) {
+        if (gx + 3 < W) {
+            uint2 u;
+            *reinterpret_cast<__half2*>(&u.x) = __floats2half2_rn(v[0], v[1]);
+            *reinterpret_cast<__half2*>(&u.y) = __floats2half2_rn(v[2], v[3]);
+            *reinterpret_cast<uint2*>(row + gx) = u;
+        }
+        return;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (gx + q < W) row[gx + q] = __float2half_rn(v[q]);
+}
+
+// stage the (kRH + 4) x (kRW + 8) window of a plane around a region (origin (oy, ox) = buf row kPadY, column kPadX) into shared memory
+template <typename TP>
+__device__ __forceinline__ void stage_window(float (*dst)[kSW], const TP* plane, int oy, int ox, int H, int W, bool vec)
+{
+    for (int i = threadIdx.x; i < kSH * (kSW / 4); i += kThreads) {
+        const int row = i / (kSW / 4), qc = i - row * (kSW / 4);
+        float v[4];
+        load_quad(plane, oy - kPadY + row, ox - kPadX + 4 * qc, H, W, vec, v);
+        *reinterpret_cast<float4*>(&dst[row][4 * qc]) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+// Jacobians of the 5x5 backward.  The recurrences have left every r^t (rhist: r^1 .. r^{T-1}; r^0 = depth) and every G^t
+// (ghist: G^0 .. G^{T-1}; G^T = grad_out) in HBM; what remains has no recurrence and is one pass:
+//   dL/dk_j(p)   = sum_ch sum_t (1 - m) G^{t+1}(p) r^t(p + o_j)          24 accumulators per pixel in registers,
+//                                                                         r^t windows double-buffered in shared memory
+//   dL/dguided_c = s_c (dL/dk_c - sum_c' s_c' dL/dk_c')                   softmax Jacobian (CSPN_ours.py:35), s recomputed
+//   dL/dx        = m * sum_{t>=1} G^t + G^0                               (CSPN_ours.py:53: the re-injected input)
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 1)
+jacobian5x5_kernel(const T* __restrict__ g, int64_t gbs, int Cg, const T* __restrict__ depth, const T* __restrict__ grad_out,
+                   const T* __restrict__ sparse, int sparse_channels, const float* __restrict__ rhist, const float* __restrict__ ghist,
+                   size_t npx, T* __restrict__ grad_guidance, T* __restrict__ grad_depth, int C, int H, int W, int iters, int vec)
+{
+    __shared__ __align__(16) float buf[2][kSH][kSW];
+    const int tid = threadIdx.x;
+    const int qx = tid % (kRW / kQuad), ry = tid / (kRW / kQuad);
+    const int b = blockIdx.z;
+    const int ox = blockIdx.x * kRW, oy = blockIdx.y * kRH;
+    const int gx = ox + qx * kQuad, gy = oy + ry;
+    const size_t hw = (size_t)H * W;
+    const bool vz = vec != 0;
+
+    float acc[kQuad][24];
+#pragma unroll
+    for (int q = 0; q < kQuad; ++q)
+#pragma unroll
+        for (int j = 0; j < 24; ++j) acc[q][j] = 0.f;
+
+    int it = 0;
+    for (int ch = 0; ch < C; ++ch) {
+        const size_t plane = (size_t)b * C + ch;
+        float mq[4] = {0.f, 0.f, 0.f, 0.f}, gsum[4] = {0.f, 0.f, 0.f, 0.f};
+        if (sparse) {
+            load_quad(sparse + ((size_t)b * sparse_channels + (sparse_channels == 1 ? 0 : ch)) * hw, gy, gx, H, W, vz, mq);
+#pragma unroll
+            for (int q = 0; q < kQuad; ++q) mq[q] = signf(mq[q]);
+        }
+        for (int t = 0; t < iters; ++t, ++it) {
+            float (*cur)[kSW] = buf[it & 1];
+            if (t == 0) stage_window(cur, depth + plane * hw, oy, ox, H, W, vz);
+            else stage_window(cur, rhist + (size_t)(t - 1) * npx + plane * hw, oy, ox, H, W, vz);
+            float G[4];
+            if (t + 1 == iters) load_quad(grad_out + plane * hw, gy, gx, H, W, vz, G);
+            else load_quad(ghist + (size_t)(t + 1) * npx + plane * hw, gy, gx, H, W, vz, G);
+            float u[4];
+#pragma unroll
+            for (int q = 0; q < kQuad; ++q) { u[q] = (1.f - mq[q]) * G[q]; gsum[q] = fmaf(mq[q], G[q], gsum[q]); }
+            __syncthreads();
+#pragma unroll
+            for (int dy = -2; dy <= 2; ++dy) {
+                const float* row = &cur[ry + kPadY + dy][kPadX + qx * kQuad];
+                float v[12];
+                unpack4(*reinterpret_cast<const float4*>(row - 4), v);
+                unpack4(*reinterpret_cast<const float4*>(row), v + 4);
+                unpack4(*reinterpret_cast<const float4*>(row + 4), v + 8);
+#pragma unroll
+                for (int dx = -2; dx <= 2; ++dx) {
+                    if (dy == 0 && dx == 0) continue;
+                    const int jj = (dy + 2) * 5 + (dx + 2);
+                    const int j = jj < 12 ? jj : jj - 1;
+#pragma unroll
+                    for (int q = 0; q < kQuad; ++q) acc[q][j] = fmaf(u[q], v[4 + q + dx], acc[q][j]);
+                }
+            }
+        }
+        if (gy < H) {
+            float G0[4];
+            load_quad(ghist + plane * hw, gy, gx, H, W, vz, G0);
+#pragma unroll
+            for (int q = 0; q < kQuad; ++q) G0[q] += gsum[q];
+            store_quad(grad_depth + plane * hw + (size_t)gy * W, gx, W, vz, G0);
+        }
+    }
+    if (gy >= H) return;
+    // softmax Jacobian, one pixel at a time (the 96 accumulators leave no room for 4 x 24 probabilities); in place
+    const T* gb = g + (size_t)b * gbs + (size_t)gy * W;
+#pragma unroll
+    for (int q = 0; q < kQuad; ++q) {
+        if (gx + q >= W) continue;
+        float mx = -INFINITY;
+        for (int j = 0; j < 24; ++j) mx = fmaxf(mx, to_f32(gb[(size_t)j * hw + gx + q]));
+        float ssum = 0.f, dot = 0.f;
+#pragma unroll
+        for (int j = 0; j < 24; ++j) {
+            const float e = fast_exp2((to_f32(gb[(size_t)j * hw + gx + q]) - mx) * 1.4426950408889634f);
+            ssum += e;
+            dot = fmaf(e, acc[q][j], dot);
+        }
+        const float inv = 1.f / ssum;
+        dot *= inv;
+#pragma unroll
+        for (int j = 0; j < 24; ++j) {
+            const float e = fast_exp2((to_f32(gb[(size_t)j * hw + gx + q]) - mx) * 1.4426950408889634f);
+            acc[q][j] = e * inv * (acc[q][j] - dot);
+        }
+    }
+    T* ggb = grad_guidance + (size_t)b * Cg * hw + (size_t)gy * W;
+#pragma unroll
+    for (int j = 0; j < 24; ++j) {
+        const float v[4] = {acc[0][j], acc[1][j], acc[2][j], acc[3][j]};
+        store_quad(ggb + (size_t)j * hw, gx, W, vz, v);
+    }
+    const float z[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = 24; j < Cg; ++j) store_quad(ggb + (size_t)j * hw, gx, W, vz, z);      // channels the forward never reads
+}
+
+template <typename T, typename TIn, bool REV>
+int launch_hist(const BwdArgs<T>& a, const TIn* rin, float* hist, long long hist_step, int steps, bool vec)
+{
+    const int out_h = kRH - 4 * steps;
+    dim3 grid((unsigned)((a.W + kOutW - 1) / kOutW), (unsigned)((a.H + out_h - 1) / out_h), (unsigned)(a.B * a.C));
+    blocked5x5_kernel<T, TIn, float, REV><<<grid, kThreads, 0, a.stream>>>(a.guidance, a.gbs, rin, a.depth, a.sparse, a.sparse_channels, (float*)nullptr,
+                                                                            hist, hist_step, steps, a.C, a.H, a.W, steps, vec ? 1 : 0);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    ++call_stats().launches;
+    return 0;
+}
 
 }  // namespace
 
@@ -220,6 +410,59 @@ int blocked5x5_forward(const FwdArgs<T>& a)
     return rc;
 }
 
+bool blocked5x5_bwd_supported(int B, int C, int H, int W, int iters, int ksize, int mode)
+{
+    return blocked5x5_supported(B, C, H, W, iters, ksize, mode) && (H + kRH - 1) / kRH <= 65535;
+}
+
+// history of both recurrences: r^1 .. r^{T-1} and G^0 .. G^{T-1}, fp32 planes
+size_t blocked5x5_bwd_workspace(int B, int C, int H, int W, int iters)
+{
+    return (size_t)(2 * iters - 1) * align256((size_t)B * C * H * W * sizeof(float));
+}
+
+// Backward of the 5x5 variant in ceil((T-1)/4) + ceil(T/4) + 1 launches (7 for T = 12) instead of the generic path's 2T + 3:
+// forward recompute and adjoint recurrence both run temporally blocked with the weights in registers and keep every
+// intermediate plane; the Jacobians are one pass over those planes.
+template <typename T>
+int blocked5x5_backward(const BwdArgs<T>& a)
+{
+    const size_t npx = (size_t)a.B * a.C * a.H * a.W;
+    const size_t need = blocked5x5_bwd_workspace(a.B, a.C, a.H, a.W, a.iters);
+    if (!a.ws || a.ws_bytes < need || ((uintptr_t)a.ws & 15)) return CSPN_ERR_WORKSPACE;
+    const size_t pstride = align256(npx * sizeof(float)) / sizeof(float);
+    float* rhist = (float*)a.ws;
+    float* ghist = rhist + (size_t)(a.iters - 1) * pstride;
+    const int vsz = 4 * (int)sizeof(T);
+    const bool vec = (a.W % 4 == 0) && ((uintptr_t)a.guidance % vsz == 0) && ((uintptr_t)a.depth % vsz == 0) && (a.gbs % 4 == 0) &&
+                     (!a.sparse || (uintptr_t)a.sparse % vsz == 0) && ((uintptr_t)a.grad_out % vsz == 0) &&
+                     ((uintptr_t)a.grad_guidance % vsz == 0) && ((uintptr_t)a.grad_depth % vsz == 0);
+    int rc = 0;
+    for (int done = 0; done < a.iters - 1 && rc == 0;) {                 // r^1 .. r^{T-1}
+        const int steps = a.iters - 1 - done < kMaxS ? a.iters - 1 - done : kMaxS;
+        if (done == 0) rc = launch_hist<T, T, false>(a, a.depth, rhist, (long long)pstride, steps, vec);
+        else rc = launch_hist<T, float, false>(a, rhist + (size_t)(done - 1) * pstride, rhist + (size_t)done * pstride, (long long)pstride, steps, vec);
+        done += steps;
+    }
+    for (int done = 0; done < a.iters && rc == 0;) {                     // G^{T-1} .. G^0
+        const int steps = a.iters - done < kMaxS ? a.iters - done : kMaxS;
+        const int tcur = a.iters - done;
+        if (done == 0) rc = launch_hist<T, T, true>(a, a.grad_out, ghist + (size_t)(tcur - 1) * pstride, -(long long)pstride, steps, vec);
+        else rc = launch_hist<T, float, true>(a, ghist + (size_t)tcur * pstride, ghist + (size_t)(tcur - 1) * pstride, -(long long)pstride, steps, vec);
+        done += steps;
+    }
+    if (rc != 0) return rc;
+    dim3 grid((unsigned)((a.W + kRW - 1) / kRW), (unsigned)((a.H + kRH - 1) / kRH), (unsigned)a.B);
+    jacobian5x5_kernel<T><<<grid, kThreads, 0, a.stream>>>(a.guidance, a.gbs, a.Cg, a.depth, a.grad_out, a.sparse, a.sparse_channels, rhist, ghist,
+                                                           pstride, a.grad_guidance, a.grad_depth, a.C, a.H, a.W, a.iters, vec ? 1 : 0);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    ++call_stats().launches;
+    return 0;
+}
+
+template int blocked5x5_backward<float>(const BwdArgs<float>&);
+template int blocked5x5_backward<__half>(const BwdArgs<__half>&);
 template int blocked5x5_forward<float>(const FwdArgs<float>&);
 template int blocked5x5_forward<__half>(const FwdArgs<__half>&);
 

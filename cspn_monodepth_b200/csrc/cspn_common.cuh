@@ -105,6 +105,10 @@ template <typename T> int dual_forward(const FwdArgs<T>& a);
 bool blocked5x5_supported(int B, int C, int H, int W, int iters, int ksize, int mode);
 template <typename T> int blocked5x5_forward(const FwdArgs<T>& a);
 size_t blocked5x5_workspace(int B, int C, int H, int W, int iters);
+// ... and its backward: both recurrences blocked with full history, Jacobians in one pass (7 launches for T = 12)
+bool blocked5x5_bwd_supported(int B, int C, int H, int W, int iters, int ksize, int mode);
+template <typename T> int blocked5x5_backward(const BwdArgs<T>& a);
+size_t blocked5x5_bwd_workspace(int B, int C, int H, int W, int iters);
 
 // fused backward (cspn_fused3x3_bwd.cu): recompute + reverse sweep + Jacobians in one launch, 3x3, one depth channel
 bool fused_bwd_supported(int C, int H, int W, int iters, int ksize, int mode);

@@ -436,6 +436,50 @@ def test_fused_backward_with_several_depth_channels():
             assert torch.count_nonzero(tg.grad[:, 8:]) == 0
 
 
+@pytest.mark.parametrize("b,cg,c,sc,h,w,iters,dtype", [(2, 24, 1, 1, 60, 80, 12, torch.float32), (1, 24, 1, 1, 100, 52, 12, torch.float32),
+                                                        (2, 26, 2, 2, 45, 61, 5, torch.float32), (1, 24, 3, 1, 33, 47, 1, torch.float32),
+                                                        (1, 24, 1, 1, 130, 9, 9, torch.float32), (2, 24, 1, 1, 96, 128, 12, torch.float16),
+                                                        (1, 24, 1, None, 70, 203, 4, torch.float32), (2, 24, 1, 1, 480, 640, 12, torch.float32)])
+def test_blocked_5x5_backward(b, cg, c, sc, h, w, iters, dtype):
+    """Backward of the 5x5 variant: forward recompute and adjoint recurrence temporally blocked (4 steps per launch, weights /
+    transposed weights in registers), Jacobians in one pass - ceil((T-1)/4) + ceil(T/4) + 1 launches, vs the C oracle's closed
+    form (pac.py:96-121 through the loop of CSPN_ours.py:47-53): ragged shapes, widths that are not a multiple of 4, several
+    depth channels with their own sparse channel, extra guidance channels (zero gradient), no sparse, fp16, one full-size image pair."""
+    g, d, s = make_inputs(500 + h + iters, b, cg, c, h, w, density=None if sc is None else 0.03, sparse_channels=sc or 1)
+    go = np.random.default_rng(c + w).standard_normal(d.shape).astype(np.float32)
+    if dtype == torch.float16:
+        g, d, s, go = (a.astype(np.float16).astype(np.float32) for a in (g, d, s, go))
+    lib = _lib.load()
+    n = lib.cspn_bwd_workspace_bytes(b, c, h, w, iters, 5, 1)
+    ws = torch.empty(n, dtype=torch.uint8, device=DEV)
+    raw = [_cu(a, dtype) for a in (go, g, d, s)]
+    gg_raw, gd_raw = torch.full_like(raw[1], float("nan")), torch.full_like(raw[2], float("nan"))
+    fn = lib.cspn_bwd_f32 if dtype == torch.float32 else lib.cspn_bwd_f16
+    rc = fn(raw[0].data_ptr(), raw[1].data_ptr(), cg * h * w, cg, raw[2].data_ptr(), None if s is None else raw[3].data_ptr(), sc or 1,
+            gg_raw.data_ptr(), gd_raw.data_ptr(), b, c, h, w, iters, 5, 1, ws.data_ptr(), n, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0 and lib.cspn_last_path() == _lib.PATH_BLOCKED
+    assert lib.cspn_last_launch_count() == (iters - 1 + 3) // 4 + (iters + 3) // 4 + 1
+    torch.cuda.synchronize()
+    gg, gd = c_oracle.backward(g[:, :24], d, s, go, iters, 5, 1, threads=0)
+    ulp = 2.0 ** -10 if dtype == torch.float16 else 0.0
+    for got, want, what in ((gd_raw, gd, "grad_depth"), (gg_raw[:, :24], gg, "grad_guidance")):
+        e = np.abs(got.float().cpu().numpy() - want)
+        tol = np.abs(want) * ulp * c + GRAD_RTOL * max(1.0, np.abs(want).max())
+        assert (e <= tol).all(), f"{what}: max err {e.max():.3e} (scale {np.abs(want).max():.3e})"
+    if cg > 24:
+        assert torch.count_nonzero(gg_raw[:, 24:]) == 0
+    # the generic multi-launch path computes the same thing
+    lib.cspn_set_path(_lib.PATH_GENERIC)
+    n2 = lib.cspn_bwd_workspace_bytes(b, c, h, w, iters, 5, 1)
+    ws2 = torch.empty(n2, dtype=torch.uint8, device=DEV)
+    gg2, gd2 = torch.empty_like(raw[1]), torch.empty_like(raw[2])
+    rc = fn(raw[0].data_ptr(), raw[1].data_ptr(), cg * h * w, cg, raw[2].data_ptr(), None if s is None else raw[3].data_ptr(), sc or 1,
+            gg2.data_ptr(), gd2.data_ptr(), b, c, h, w, iters, 5, 1, ws2.data_ptr(), n2, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0 and lib.cspn_last_path() == _lib.PATH_GENERIC
+    scale = max(1.0, float(gg2.float().abs().max()))
+    assert float((gg2.float() - gg_raw.float()).abs().max()) <= (2 * GRAD_RTOL + 4 * ulp) * scale
+
+
 def test_pipelined_host_entry_points():
     """cspn_fwd_host_submit_* / cspn_host_wait: several calls in flight (H2D of one overlaps kernel + D2H of the previous),
     every result checked against the oracle; fp32 with a strided 12-channel guidance and fp16; tickets are per call."""
