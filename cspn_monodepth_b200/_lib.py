@@ -32,6 +32,11 @@ SIGNATURES = {
     "cspn_fwd_host_submit_f32": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_int, _c_vp] + [_c_int] * 7 + [ctypes.POINTER(_c_int)]),
     "cspn_fwd_host_submit_f16": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_int, _c_vp] + [_c_int] * 7 + [ctypes.POINTER(_c_int)]),
     "cspn_host_wait": (_c_int, [_c_int]),
+    "cspn_heads_workspace_bytes": (_c_sz, []),
+    "cspn_heads_fwd_f32": (_c_int, [_c_vp] * 5 + [_c_int] * 8 + [_c_vp]),
+    "cspn_heads_fwd_f16": (_c_int, [_c_vp] * 5 + [_c_int] * 8 + [_c_vp]),
+    "cspn_heads_bwd_f32": (_c_int, [_c_vp] * 8 + [_c_int] * 8 + [_c_vp, _c_sz, _c_vp]),
+    "cspn_heads_bwd_f16": (_c_int, [_c_vp] * 8 + [_c_int] * 8 + [_c_vp, _c_sz, _c_vp]),
     "cspn_legacy_workspace_bytes": (_c_sz, [_c_int] * 4),
     "cspn_legacy_fwd_f32": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp] + [_c_int] * 4 + [_c_vp, _c_sz, _c_vp]),
     "cspn_legacy_fwd_f16": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp] + [_c_int] * 4 + [_c_vp, _c_sz, _c_vp]),

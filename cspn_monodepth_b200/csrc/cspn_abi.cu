@@ -136,6 +136,29 @@ int backward_impl(const T* grad_out, const T* guidance, int64_t gbs, int Cg, con
 }
 
 template <typename T>
+int heads_fwd_impl(const T* x, const T* w1, const T* w2, T* out1, T* out2, int B, int Cin, int h, int w, int H, int W, int n1, int n2, void* stream)
+{
+    if (B < 0 || !heads_supported(n1, n2, Cin, h, w, H, W)) return CSPN_ERR_BAD_SHAPE;
+    if (B == 0) return CSPN_OK;
+    if (!x || !w1 || !out1 || (n2 > 0 && (!w2 || !out2))) return CSPN_ERR_NULL_POINTER;
+    call_stats().launches = 0;
+    return heads_forward<T>(x, w1, w2, out1, out2, n1, n2, B, Cin, h, w, H, W, (cudaStream_t)stream);
+}
+
+template <typename T>
+int heads_bwd_impl(const T* x, const T* w1, const T* w2, const T* go1, const T* go2, T* gx, T* gw1, T* gw2, int B, int Cin, int h, int w, int H, int W,
+                   int n1, int n2, void* ws, size_t ws_bytes, void* stream)
+{
+    if (B < 0 || !heads_supported(n1, n2, Cin, h, w, H, W)) return CSPN_ERR_BAD_SHAPE;
+    if (B == 0) return CSPN_OK;
+    if (!x || !w1 || !go1 || (n2 > 0 && (!w2 || !go2))) return CSPN_ERR_NULL_POINTER;
+    if (gw1 && n2 > 0 && !gw2) return CSPN_ERR_NULL_POINTER;
+    if (gw1 && (!ws || ws_bytes < heads_workspace_bytes() || ((uintptr_t)ws & 15))) return CSPN_ERR_WORKSPACE;
+    call_stats().launches = 0;
+    return heads_backward<T>(x, w1, w2, go1, go2, gx, gw1, gw2, n1, n2, B, Cin, h, w, H, W, ws, (cudaStream_t)stream);
+}
+
+template <typename T>
 int legacy_impl(const T* guidance, int64_t gbs, const T* depth, const T* sparse, T* out, int B, int H, int W, int iters, void* ws, size_t ws_bytes,
                 void* stream)
 {
@@ -456,6 +479,28 @@ int cspn_fwd_host_f32(const float* guidance, int64_t gbs, const float* depth, co
                       float* out, int B, int C, int H, int W, int iters, int ksize, int mode, void* stream)
 {
     return forward_host_impl<float>(guidance, gbs, depth, sparse, sparse_channels, out, B, C, H, W, iters, ksize, mode, stream);
+}
+size_t cspn_heads_workspace_bytes(void) { return heads_workspace_bytes(); }
+int cspn_heads_fwd_f32(const float* x, const float* w1, const float* w2, float* out1, float* out2, int B, int Cin, int h, int w, int H, int W, int n1, int n2,
+                       void* stream)
+{
+    return heads_fwd_impl<float>(x, w1, w2, out1, out2, B, Cin, h, w, H, W, n1, n2, stream);
+}
+int cspn_heads_fwd_f16(const void* x, const void* w1, const void* w2, void* out1, void* out2, int B, int Cin, int h, int w, int H, int W, int n1, int n2,
+                       void* stream)
+{
+    return heads_fwd_impl<__half>((const __half*)x, (const __half*)w1, (const __half*)w2, (__half*)out1, (__half*)out2, B, Cin, h, w, H, W, n1, n2, stream);
+}
+int cspn_heads_bwd_f32(const float* x, const float* w1, const float* w2, const float* go1, const float* go2, float* gx, float* gw1, float* gw2, int B, int Cin,
+                       int h, int w, int H, int W, int n1, int n2, void* ws, size_t ws_bytes, void* stream)
+{
+    return heads_bwd_impl<float>(x, w1, w2, go1, go2, gx, gw1, gw2, B, Cin, h, w, H, W, n1, n2, ws, ws_bytes, stream);
+}
+int cspn_heads_bwd_f16(const void* x, const void* w1, const void* w2, const void* go1, const void* go2, void* gx, void* gw1, void* gw2, int B, int Cin,
+                       int h, int w, int H, int W, int n1, int n2, void* ws, size_t ws_bytes, void* stream)
+{
+    return heads_bwd_impl<__half>((const __half*)x, (const __half*)w1, (const __half*)w2, (const __half*)go1, (const __half*)go2, (__half*)gx, (__half*)gw1,
+                                  (__half*)gw2, B, Cin, h, w, H, W, n1, n2, ws, ws_bytes, stream);
 }
 size_t cspn_legacy_workspace_bytes(int B, int H, int W, int iters)
 {

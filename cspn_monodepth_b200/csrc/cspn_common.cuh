@@ -115,6 +115,14 @@ bool fused_bwd_supported(int C, int H, int W, int iters, int ksize, int mode);
 template <typename T> int fused_backward(const BwdArgs<T>& a);
 size_t fused_bwd_workspace(int B, int C, int H, int W, int iters);
 
+// the two output heads upstream of the module (cspn_heads.cu): unpool x2 + conv3x3 without the zeros, both heads in one pass
+size_t heads_workspace_bytes();
+bool heads_supported(int n1, int n2, int Cin, int h, int w, int H, int W);
+template <typename T> int heads_forward(const T* x, const T* w1, const T* w2, T* out1, T* out2, int n1, int n2, int B, int Cin, int h, int w, int H, int W,
+                                        cudaStream_t stream);
+template <typename T> int heads_backward(const T* x, const T* w1, const T* w2, const T* go1, const T* go2, T* gx, T* gw1, T* gw2, int n1, int n2, int B,
+                                         int Cin, int h, int w, int H, int W, void* ws, cudaStream_t stream);
+
 // legacy max-of-8 CSPN (cspn_legacy.cu): temporally blocked forward, 4 steps per launch
 size_t legacy_workspace(int B, int H, int W, int iters);
 template <typename T> int legacy_forward(const T* guidance, int64_t gbs, const T* depth, const T* sparse, T* out, int B, int H, int W, int iters,

@@ -5,7 +5,7 @@
   ``from network.libs.post_process.CSPN_new import AffinityPropagate`` (``unet_cspn_nyu.py:9``) and
   ``from network.libs.post_process.CSPN_ours import AffinityPropagate`` (``unet_ours.py:16``) pick them up.
   Call it before importing the UNet files.
-* :func:`patch_model` swaps ``model.post_process_layer`` on an already-built reference model
+* :func:`patch_model` (``heads=True``: also the two output heads upstream, see :mod:`cspn_monodepth_b200.heads`) swaps ``model.post_process_layer`` on an already-built reference model
   (``unet_cspn_nyu.py:357-358`` / ``unet_ours.py:304-305``).  The module has no parameters or buffers,
   so checkpoints are unaffected.
 """
@@ -22,8 +22,15 @@ def install():
         pkg.CSPN_new, pkg.CSPN_ours = cspn_new, cspn_ours
 
 
-def patch_model(model):
-    """Replace every reference ``AffinityPropagate`` inside ``model`` by the B200 one. Returns the count."""
+def patch_model(model, heads=False):
+    """Replace every reference ``AffinityPropagate`` inside ``model`` by the B200 one. Returns the count.
+
+    ``heads=True`` also replaces the two ``Simple_Gudi_UpConv_Block_Last_Layer`` heads that feed it
+    (``gud_up_proj_layer5`` / ``gud_up_proj_layer6``, ``unet_cspn_nyu.py:331-332`` / ``unet_ours.py:278-279``) by the fused B200
+    heads of :mod:`cspn_monodepth_b200.heads` (one launch for both, parameters kept)."""
+    if heads and hasattr(model, "gud_up_proj_layer5") and hasattr(model, "gud_up_proj_layer6"):
+        from .heads import fuse_heads
+        fuse_heads(model)
     n = 0
     for parent in model.modules():
         for name, child in list(parent.named_children()):

@@ -155,6 +155,27 @@ CSPN_API int cspn_fwd_host_submit_f16(const void* guidance, int64_t guidance_bat
 CSPN_API int cspn_host_wait(int ticket);
 CSPN_API int cspn_host_pipeline_depth(void);
 
+/* ---- the two output heads directly upstream of the module ---------------------------------------------
+ * Simple_Gudi_UpConv_Block_Last_Layer, network/unet_cspn_nyu.py:195-218 (instances :331-332, applied to the same x at :383-384)
+ * and network/unet_ours.py:194-202 (:278-279, :331-332): 2x unpooling by zero insertion, cropped to H x W (H <= 2h, W <= 2w),
+ * then conv3x3 (padding 1, no bias).  One pass over x [B,Cin,h,w] for BOTH heads: weights w1 [n1,Cin,3,3] -> out1 [B,n1,H,W]
+ * (the blur depth, n1 = 1) and w2 [n2,Cin,3,3] -> out2 [B,n2,H,W] (the guidance, n2 = 8 / 12); n2 = 0 with w2 = out2 = NULL runs
+ * a single head.  n1 >= 1, n1 + n2 <= 16, Cin <= 256.  The zeros of the unpooled tensor are never materialised or multiplied.
+ * Backward: go1 / go2 are the gradients of out1 / out2; writes gx [B,Cin,h,w] (skipped when NULL) and gw1 / gw2 (skipped when
+ * gw1 is NULL; deterministic split-K reduction through `workspace`, cspn_heads_workspace_bytes() bytes, 16-byte aligned).
+ * Same conventions as cspn_fwd_* (device pointers, stream-ordered, no allocation, graph-capturable). */
+CSPN_API size_t cspn_heads_workspace_bytes(void);
+CSPN_API int cspn_heads_fwd_f32(const float* x, const float* w1, const float* w2, float* out1, float* out2,
+                                int B, int Cin, int h, int w, int H, int W, int n1, int n2, void* stream);
+CSPN_API int cspn_heads_fwd_f16(const void* x, const void* w1, const void* w2, void* out1, void* out2,
+                                int B, int Cin, int h, int w, int H, int W, int n1, int n2, void* stream);
+CSPN_API int cspn_heads_bwd_f32(const float* x, const float* w1, const float* w2, const float* go1, const float* go2,
+                                float* gx, float* gw1, float* gw2, int B, int Cin, int h, int w, int H, int W, int n1, int n2,
+                                void* workspace, size_t workspace_bytes, void* stream);
+CSPN_API int cspn_heads_bwd_f16(const void* x, const void* w1, const void* w2, const void* go1, const void* go2,
+                                void* gx, void* gw1, void* gw2, int B, int Cin, int h, int w, int H, int W, int n1, int n2,
+                                void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- legacy max-of-8 CSPN ---------------------------------------------------------------------------
  * network/libs/post_process/CSPN.py:19-56, AffinityPropagate().forward(guidance, blur_depth, sparse_depth), and :132-164,
  * AffinityPropagate_prediction().forward(guidance, blur_depth) (sparse == NULL).  Per step and gate k = 0..7 (|guidance[:,k]|,

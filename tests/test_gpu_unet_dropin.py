@@ -45,15 +45,23 @@ def _rgbd(batch, seed):
     return torch.cat([rgb, dense * mask], dim=1).to(DEV), target.to(DEV)      # the reference's rgbd input: channel 3 = sparse depth
 
 
+@pytest.mark.parametrize("heads", [False, True])
 @pytest.mark.parametrize("which", ["unet_cspn_nyu", "unet_ours"])
-def test_reference_unet_with_b200_module(which):
+def test_reference_unet_with_b200_module(which, heads):
+    """heads=True: the two output heads upstream of the module (unet_cspn_nyu.py:331-332,383-384) are replaced as well - one
+    fused launch of csrc/cspn_heads.cu for both; the reference's own heads then run as exact fp32 convolutions (TF32 off) so
+    that the comparison is against the reference's arithmetic, not cuDNN's TF32 shortcut."""
     unet_cspn_nyu, unet_ours = _import_reference()
     torch.manual_seed(7)
     torch.backends.cudnn.benchmark = False
     torch.backends.cudnn.deterministic = True
+    torch.backends.cudnn.allow_tf32 = not heads
     ref_model = (unet_cspn_nyu if which == "unet_cspn_nyu" else unet_ours).resnet50(pretrained=False).to(DEV).train()
     our_model = copy.deepcopy(ref_model)
-    assert dropin.patch_model(our_model) == 1
+    assert dropin.patch_model(our_model, heads=heads) == 1
+    if heads:
+        from cspn_monodepth_b200.heads import Simple_Gudi_UpConv_Block_Last_Layer as OurHead
+        assert isinstance(our_model.gud_up_proj_layer5, OurHead) and isinstance(our_model.gud_up_proj_layer6, OurHead)
     assert isinstance(our_model.post_process_layer, (cspn_new.AffinityPropagate, cspn_ours.AffinityPropagate))
     assert type(ref_model.post_process_layer).__module__.startswith("network.libs.post_process")
     assert our_model.state_dict().keys() == ref_model.state_dict().keys()       # the module has no parameters or buffers
