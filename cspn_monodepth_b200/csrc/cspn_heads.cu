@@ -20,7 +20,7 @@ namespace {
 
 constexpr int kHT = 128;                  // threads per CTA (forward, backward x)
 constexpr int kTR = 8, kTC = 32;          // cell tile of the forward / backward-x kernels
-constexpr int kCK = 16;                   // input channels per shared-memory chunk (forward)
+constexpr int kCK = 8;                    // input channels per shared-memory chunk (forward), double-buffered
 constexpr int kXP = 36;                   // pitch of a staged x row (33 columns)
 constexpr int kNOP = 16;                  // outputs padded to 16 in shared memory
 constexpr int kMaxCin = 256;
@@ -46,13 +46,13 @@ heads_fwd_kernel(const T* __restrict__ x, const T* __restrict__ w1, const T* __r
 {
     extern __shared__ __align__(16) float smem[];
     float* wsm = smem;                                    // [Cin][9][kNOP]
-    float* xs = smem + (size_t)Cin * 9 * kNOP;            // [kCK][kTR + 1][kXP]
+    float* xs = smem + (size_t)Cin * 9 * kNOP;            // [2][kCK][kTR + 1][kXP]
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int b = blockIdx.z, i0 = blockIdx.y * kTR, j0 = blockIdx.x * kTC;
     const int hs = (H + 1) >> 1, ws = (W + 1) >> 1;      // cells that survive the crop + mask
-    for (int idx = tid; idx < Cin * 9 * kNOP; idx += kHT) {
-        const int o = idx % kNOP, tap = (idx / kNOP) % 9, c = idx / (9 * kNOP);
-        wsm[idx] = o < NO ? w_at(w1, w2, n1, n2, Cin, o, c, tap) : 0.f;
+    for (int idx = tid; idx < kNOP * Cin * 9; idx += kHT) {                // global order (o, c, tap): coalesced reads
+        const int o = idx / (Cin * 9), ct = idx - o * (Cin * 9);
+        wsm[ct * kNOP + o] = o < NO ? w_at(w1, w2, n1, n2, Cin, o, ct / 9, ct % 9) : 0.f;
     }
     float acc[2][4][NO];
 #pragma unroll
@@ -63,19 +63,47 @@ heads_fwd_kernel(const T* __restrict__ x, const T* __restrict__ w1, const T* __r
             for (int o = 0; o < NO; ++o) acc[a][p][o] = 0.f;
 
     const T* xb = x + (size_t)b * Cin * h * w;
-    for (int c0 = 0; c0 < Cin; c0 += kCK) {
-        __syncthreads();                                  // previous chunk consumed (first pass: weights may still be filling - fine)
-        for (int idx = tid; idx < kCK * (kTR + 1) * 33; idx += kHT) {
-            const int col = idx % 33, r = (idx / 33) % (kTR + 1), c = idx / (33 * (kTR + 1));
-            const int i = i0 + r, j = j0 + col;
-            float v = 0.f;
-            if (c0 + c < Cin && i < hs && j < ws) v = to_f32(xb[((size_t)(c0 + c) * h + i) * w + j]);
-            xs[(c * (kTR + 1) + r) * kXP + col] = v;
+    // stage one chunk of x: (kCK channels) x (kTR + 1 rows) x 33 columns; a warp takes whole rows (one coalesced 128-byte
+    // request + the 33rd column), fp32 goes straight to shared memory with cp.async (zero-filled outside the kept cells)
+    auto stage = [&](int c0, float* dst) {
+        const int lane = tid & 31, warp = tid >> 5;
+        for (int row = warp; row < kCK * (kTR + 1); row += kHT / 32) {
+            const int c = row / (kTR + 1), r = row - c * (kTR + 1);
+            const int i = i0 + r;
+            const bool row_ok = c0 + c < Cin && i < hs;
+            const T* src = xb + ((size_t)(row_ok ? c0 + c : 0) * h + (row_ok ? i : 0)) * w;
+            float* d = dst + row * kXP;
+#pragma unroll
+            for (int rep = 0; rep < 2; ++rep) {
+                const int col = rep == 0 ? lane : 32;
+                if (rep == 1 && lane != 0) break;
+                const bool ok = row_ok && j0 + col < ws;
+                if (sizeof(T) == 4) {
+                    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(d + col);
+                    const void* ga = ok ? (const void*)(src + j0 + col) : (const void*)xb;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sa), "l"(ga), "r"(ok ? 4 : 0) : "memory");
+                } else {
+                    d[col] = ok ? to_f32(src[j0 + col]) : 0.f;
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const int nchunks = (Cin + kCK - 1) / kCK;
+    stage(0, xs);
+    for (int ck = 0; ck < nchunks; ++ck) {
+        const int c0 = ck * kCK;
+        float* cur = xs + (ck & 1) * (kCK * (kTR + 1) * kXP);
+        if (ck + 1 < nchunks) {
+            stage(c0 + kCK, xs + ((ck + 1) & 1) * (kCK * (kTR + 1) * kXP));
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
         const int nc = Cin - c0 < kCK ? Cin - c0 : kCK;
         for (int c = 0; c < nc; ++c) {
-            const float* r0 = xs + (c * (kTR + 1) + ty) * kXP + 2 * tx;
+            const float* r0 = cur + (c * (kTR + 1) + ty) * kXP + 2 * tx;
             const float* r1 = r0 + kXP;
             const float xa[2][4] = {{r0[0], r0[1], r1[0], r1[1]}, {r0[1], r0[2], r1[1], r1[2]}};     // {self, right, down, diagonal} of cells A, B
             const float* wc = wsm + (size_t)(c0 + c) * 9 * kNOP;
@@ -102,6 +130,7 @@ heads_fwd_kernel(const T* __restrict__ x, const T* __restrict__ w1, const T* __r
                     acc[a][3][o] = fmaf(wt[8][o], xa[a][3], fmaf(wt[6][o], xa[a][2], fmaf(wt[2][o], xa[a][1], fmaf(wt[0][o], xa[a][0], acc[a][3][o]))));
                 }
         }
+        __syncthreads();                                  // this buffer is staged again two chunks later
     }
     // 4 adjacent output pixels per (output channel, parity row): columns 2 (j0 + 2 tx) .. + 3
     const int i = i0 + ty, X0 = 2 * (j0 + 2 * tx);
@@ -153,9 +182,9 @@ heads_bwd_x_kernel(const T* __restrict__ go1, const T* __restrict__ go2, const T
     const int b = blockIdx.z / nchunk, c0 = (blockIdx.z % nchunk) * kBC;
     const int i0 = blockIdx.y * kTR, j0 = blockIdx.x * kTC;
     const size_t HW = (size_t)H * W;
-    for (int idx = tid; idx < NO * 9 * kBC; idx += kHT) {
-        const int c = idx % kBC, tap = (idx / kBC) % 9, o = idx / (9 * kBC);
-        wsm[idx] = c0 + c < Cin ? w_at(w1, w2, n1, n2, Cin, o, c0 + c, tap) : 0.f;
+    for (int idx = tid; idx < NO * kBC * 9; idx += kHT) {                  // global order (o, c, tap): coalesced reads
+        const int o = idx / (kBC * 9), ct = idx - o * (kBC * 9), c = ct / 9, tap = ct - 9 * c;
+        wsm[(o * 9 + tap) * kBC + c] = c0 + c < Cin ? w_at(w1, w2, n1, n2, Cin, o, c0 + c, tap) : 0.f;
     }
     for (int idx = tid; idx < NO * kGR * 66; idx += kHT) {
         const int col = idx % 66, r = (idx / 66) % kGR, o = idx / (66 * kGR);
@@ -297,7 +326,7 @@ template <typename T, int NO>
 int heads_forward_no(const T* x, const T* w1, const T* w2, T* out1, T* out2, int n1, int n2, int B, int Cin, int h, int w, int H, int W, cudaStream_t stream)
 {
     auto kern = heads_fwd_kernel<T, NO>;
-    const size_t smem = ((size_t)Cin * 9 * kNOP + (size_t)kCK * (kTR + 1) * kXP) * sizeof(float);
+    const size_t smem = ((size_t)Cin * 9 * kNOP + (size_t)2 * kCK * (kTR + 1) * kXP) * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     const int hs = (H + 1) / 2, ws = (W + 1) / 2;
