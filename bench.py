@@ -550,18 +550,177 @@ def extra_rows(dev, rank, world, dist, peak):
             extra[name] = {"error": repr(exc)[:200]}
         torch.cuda.empty_cache()
     # forward + backward (BASELINE.json configs[2] is forward+backward): algorithmic bytes 11 + 20 elements per pixel
-    for name, c, st in (("kitti_b32_1216x352_f16_fwd_bwd", KITTI, 10), ("nyu_b8_304x228_f32_fwd_bwd", NYU, 100)):
+    # (5x5: 27 forward + 52 backward elements: 24 + 1 + 1 + 1 read, 24 + 1 written)
+    for name, c, st, elems in (("kitti_b32_1216x352_f16_fwd_bwd", KITTI, 10, 31), ("nyu_b8_304x228_f32_fwd_bwd", NYU, 100, 31),
+                               ("pac5x5_b16_640x480_f32_fwd_bwd", PAC5, 5, 79)):
         try:
             ms, ln = time_fwd_bwd(c, dev, st)
             ms = agg(ms)
             px = c["B"] * c["H"] * c["W"]
             es = 4 if c["dtype"] == "f32" else 2
             extra[name] = {"value": world * px / (ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms, "launches_per_step": ln,
-                           "roofline_frac": 31 * es * px / (ms * 1e-3) / 1e9 / peak, "n_gpus": world, "per_gpu_batch": c["B"]}
+                           "roofline_frac": elems * es * px / (ms * 1e-3) / 1e9 / peak, "n_gpus": world, "per_gpu_batch": c["B"]}
         except Exception as exc:
             extra[name] = {"error": repr(exc)[:200]}
         torch.cuda.empty_cache()
+    if world == 1:
+        try:
+            extra.update(neighbour_rows(dev))
+        except Exception as exc:
+            extra["neighbour_rows_error"] = repr(exc)[:200]
+        torch.cuda.empty_cache()
+    try:
+        extra["unet_train_step"] = unet_train_step(dev, rank, world, dist)
+    except Exception as exc:
+        extra["unet_train_step"] = {"error": repr(exc)[:200]}
+    torch.cuda.empty_cache()
     return extra
+
+
+def _event_ms(fn, reps, dev):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    return e0.elapsed_time(e1) / reps
+
+
+def neighbour_rows(dev):
+    """what sits either side of the module, at the headline batch (8 x 304x228 fp32), eager launches timed with
+    CUDA events: the two output heads (upstream), masked-L1 loss and metrics (downstream), the legacy max-of-8 CSPN, and the
+    whole tail of unet_cspn_nyu's forward + backward (heads -> CSPN-24 -> loss) with the reference's formulation beside it."""
+    import torch.nn.functional as F
+    from cspn_monodepth_b200 import criteria, cspn_legacy, cspn_new, heads
+    rows = {}
+    b, cin, h, w, H, W, ng = NYU["B"], 64, 114, 152, NYU["H"], NYU["W"], 12
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(b, cin, h, w, generator=gen).to(dev).requires_grad_(True)
+    wd = (torch.randn(1, cin, 3, 3, generator=gen) / 24).to(dev).requires_grad_(True)
+    wg = (torch.randn(ng, cin, 3, 3, generator=gen) / 24).to(dev).requires_grad_(True)
+    sparse = ((torch.rand(b, 1, H, W, generator=gen) < 500.0 / 69312.0) * (torch.rand(b, 1, H, W, generator=gen) * 10 + 0.1)).to(dev)
+    target = (torch.rand(b, 1, H, W, generator=gen) * 9.5 + 0.5).to(dev)
+    px = b * H * W
+
+    def ref_heads():
+        k = torch.zeros(cin, 1, 2, 2, device=dev)
+        k[:, :, 0, 0] = 1
+        u = F.conv_transpose2d(x, k, stride=2, groups=cin)[:, :, :H, :W]      # unet_ours.py:138-150 (the NYU file builds its mask in a Python loop)
+        return F.conv2d(u, wd, padding=1), F.conv2d(u, wg, padding=1)
+
+    with torch.no_grad():
+        ms = _event_ms(lambda: heads.guidance_depth_heads(x, wd, wg, H, W), 50, dev)
+        tf32 = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        ms_ref = _event_ms(ref_heads, 10, dev)
+        d_ref, g_ref = ref_heads()
+        torch.backends.cudnn.allow_tf32 = tf32
+        d, g = heads.guidance_depth_heads(x, wd, wg, H, W)
+    rows["heads_nyu_b8_f32_fwd"] = {"value": px / (ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms, "launches_per_step": 1,
+                                    "useful_tflops": 2.0 * b * h * w * 9 * cin * (1 + ng) / (ms * 1e-3) / 1e12,
+                                    "roofline_frac_hbm": 4.0 * (b * cin * h * w + (1 + ng) * px) / (ms * 1e-3) / 1e9 / hbm_peak()[0],
+                                    "torch_cudnn_fp32_ms": ms_ref, "max_abs_vs_torch_fp32": max(float((d - d_ref).abs().max()), float((g - g_ref).abs().max())),
+                                    "what": "both heads (64 -> 1 + 12 channels) in one launch of csrc/cspn_heads.cu vs conv_transpose2d + 2 x conv2d (cuDNN, TF32 off)"}
+    god, gog = torch.randn_like(d), torch.randn_like(g)
+
+    def heads_train():
+        dd, gg = heads.guidance_depth_heads(x, wd, wg, H, W)
+        torch.autograd.backward([dd, gg], [god, gog])
+    rows["heads_nyu_b8_f32_fwd_bwd"] = {"ms_per_step": _event_ms(heads_train, 20, dev), "launches_per_step": 4}
+    # legacy max-of-8 CSPN, 16 steps (CSPN.py)
+    with torch.no_grad():
+        gd_ = g[:, :8].contiguous()
+        ms = _event_ms(lambda: cspn_legacy.legacy_propagate(gd_, d, sparse, 16), 50, dev)
+    rows["legacy_cspn16_nyu_b8_f32_fwd"] = {"value": px / (ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms, "launches_per_step": 4,
+                                            "roofline_frac": 44.0 * px / (ms * 1e-3) / 1e9 / hbm_peak()[0]}
+    # masked L1 loss (fwd + bwd) and the 10 metrics: 8 / 12 / 8 bytes per pixel
+    pred = (target + 0.3 * torch.randn_like(target)).abs().add(0.05).requires_grad_(True)
+    crit = criteria.MaskedL1Loss()
+
+    def loss_step():
+        pred.grad = None
+        crit(pred, target).backward()
+    ms_l = _event_ms(loss_step, 50, dev)
+    with torch.no_grad():
+        ms_m = _event_ms(lambda: criteria.evaluate_device(pred, target), 50, dev)
+    rows["masked_l1_fwd_bwd_and_metrics_nyu_b8"] = {"loss_fwd_bwd_ms": ms_l, "metrics_ms": ms_m, "launches": "1 + 1, 1",
+                                                    "what": "eager Python calls: the kernels stream 4.4 MB, the time is launch + autograd overhead"}
+    # the tail of unet_cspn_nyu.ResNet.forward (:383-386) + criterion, forward + backward
+    prop = cspn_new.AffinityPropagate(24, 3)
+
+    def tail_ours():
+        x.grad = wd.grad = wg.grad = None
+        dd, gg = heads.guidance_depth_heads(x, wd, wg, H, W)
+        crit(prop(gg, dd, sparse), target).backward()
+    rows["unet_tail_nyu_b8_f32_train"] = {"ms_per_step": _event_ms(tail_ours, 20, dev),
+                                          "what": "heads -> CSPN-24 -> masked L1, forward + backward: 1 + 1 + 1 forward launches, 1 + 1 + 4 backward"}
+    fn, kind, _ = reference_forward(NYU)
+    if kind == "reference":
+        def tail_ref():
+            x.grad = wd.grad = wg.grad = None
+            dd, gg = ref_heads()
+            y = fn(gg, dd, sparse)
+            valid = target > 0
+            (target - y)[valid].abs().mean().backward()
+        try:
+            rows["unet_tail_nyu_b8_f32_train"]["reference_formulation_ms"] = _event_ms(tail_ref, 3, dev)
+        except Exception as exc:
+            rows["unet_tail_nyu_b8_f32_train"]["reference_error"] = repr(exc)[:160]
+    return rows
+
+
+def unet_train_step(dev, rank, world, dist):
+    """BASELINE.json configs[4] "NCCL grad all-reduce only": one training step of the reference's own unet_cspn_nyu (staged under
+    baseline/_ref, ResNet-50 encoder, 256 M parameters - resnet18 does not build in the reference) with the B200 heads + CSPN module dropped in, batch 8 per GPU; with N > 1 the model is
+    wrapped in DistributedDataParallel - the only collective is its gradient all-reduce, the CSPN path itself issues none."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "network")):
+        return {"unavailable": "baseline/_ref is not staged"}
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+    from network import unet_cspn_nyu
+    from cspn_monodepth_b200 import criteria, dropin
+    torch.manual_seed(11)
+    model = unet_cspn_nyu.resnet50(pretrained=False).to(dev).train()
+    dropin.patch_model(model, heads=True)
+    ddp = model
+    if dist is not None:
+        from torch.nn.parallel import DistributedDataParallel
+        ddp = DistributedDataParallel(model, device_ids=[dev.index])
+    opt = torch.optim.SGD(ddp.parameters(), lr=1e-3, momentum=0.9)
+    crit = criteria.MaskedL1Loss()
+    gen = torch.Generator().manual_seed(100 + rank)
+    rgb = torch.rand(8, 3, 228, 304, generator=gen)
+    dense = torch.rand(8, 1, 228, 304, generator=gen) * 9 + 0.5
+    mask = torch.rand(8, 1, 228, 304, generator=gen) < 500.0 / 69312.0
+    xin, target = torch.cat([rgb, dense * mask], dim=1).to(dev), dense.to(dev)
+    losses = []
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        loss = crit(ddp(xin), target)
+        loss.backward()
+        opt.step()
+        losses.append(loss.detach())
+    ms = _event_ms(step, 3, dev)
+    out = {"ms_per_step": ms, "images_per_s": world * 8 / (ms * 1e-3), "n_gpus": world, "per_gpu_batch": 8,
+           "loss_first_last": [float(losses[0]), float(losses[-1])],
+           "what": "reference unet_cspn_nyu.resnet50 (its decoder blocks still build their unpooling masks in Python loops) + B200 heads / CSPN-24 / masked-L1 kernels, SGD step" + (", DDP gradient all-reduce over NCCL" if dist is not None else "")}
+    if dist is not None:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out["ms_per_step"] = float(t.item())
+        out["images_per_s"] = world * 8 / (out["ms_per_step"] * 1e-3)
+        p0 = next(model.parameters()).detach().flatten()[:1024].clone()
+        lo, hi = p0.clone(), p0.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        out["replicas_in_sync"] = bool(torch.equal(lo, hi))
+    return out
 
 
 def main():
