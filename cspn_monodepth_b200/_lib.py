@@ -32,6 +32,12 @@ SIGNATURES = {
     "cspn_fwd_host_submit_f32": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_int, _c_vp] + [_c_int] * 7 + [ctypes.POINTER(_c_int)]),
     "cspn_fwd_host_submit_f16": (_c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_int, _c_vp] + [_c_int] * 7 + [ctypes.POINTER(_c_int)]),
     "cspn_host_wait": (_c_int, [_c_int]),
+    "cspn_abn_workspace_bytes": (_c_sz, [_c_int]),
+    "cspn_abn_stats_f32": (_c_int, [_c_vp, _c_int, _c_int, _c_int, _c_vp, _c_vp, _c_sz, _c_vp]),
+    "cspn_abn_finalize_f32": (_c_int, [_c_vp, ctypes.c_double, _c_vp, _c_vp, _c_vp, _c_vp, ctypes.c_float, _c_int, _c_vp]),
+    "cspn_abn_forward_f32": (_c_int, [_c_vp] * 5 + [_c_int] * 3 + [ctypes.c_float, _c_int, ctypes.c_float, _c_vp]),
+    "cspn_abn_bwd_reduce_f32": (_c_int, [_c_vp] * 4 + [_c_int] * 3 + [ctypes.c_float, _c_int, ctypes.c_float, _c_vp, _c_vp, _c_sz, _c_vp]),
+    "cspn_abn_bwd_apply_f32": (_c_int, [_c_vp] * 7 + [ctypes.c_double, ctypes.c_double, _c_vp, _c_vp] + [_c_int] * 3 + [ctypes.c_float, _c_int, ctypes.c_float, _c_vp]),
     "cspn_heads_workspace_bytes": (_c_sz, []),
     "cspn_heads_fwd_f32": (_c_int, [_c_vp] * 5 + [_c_int] * 8 + [_c_vp]),
     "cspn_heads_fwd_f16": (_c_int, [_c_vp] * 5 + [_c_int] * 8 + [_c_vp]),

@@ -480,6 +480,53 @@ int cspn_fwd_host_f32(const float* guidance, int64_t gbs, const float* depth, co
 {
     return forward_host_impl<float>(guidance, gbs, depth, sparse, sparse_channels, out, B, C, H, W, iters, ksize, mode, stream);
 }
+static int abn_shape_ok(int N, int C, int S, int act)
+{
+    return N >= 1 && C >= 1 && S >= 1 && (long)N * C <= 2147483647l && act >= 0 && act <= 2;
+}
+size_t cspn_abn_workspace_bytes(int C) { return C < 1 ? 0 : abn_workspace_bytes(C); }
+int cspn_abn_stats_f32(const float* x, int N, int C, int S, double* sums, void* ws, size_t ws_bytes, void* stream)
+{
+    if (!abn_shape_ok(N, C, S, 0)) return CSPN_ERR_BAD_SHAPE;
+    if (!x || !sums) return CSPN_ERR_NULL_POINTER;
+    if (!ws || ws_bytes < abn_workspace_bytes(C) || ((uintptr_t)ws & 7)) return CSPN_ERR_WORKSPACE;
+    call_stats().launches = 0;
+    return abn_stats(x, N, C, S, sums, ws, (cudaStream_t)stream);
+}
+int cspn_abn_finalize_f32(const double* sums, double count, float* mean, float* var, float* running_mean, float* running_var, float momentum, int C,
+                          void* stream)
+{
+    if (C < 1 || !(count >= 1.0)) return CSPN_ERR_BAD_SHAPE;
+    if (!sums || !mean || !var) return CSPN_ERR_NULL_POINTER;
+    call_stats().launches = 0;
+    return abn_finalize(sums, count, mean, var, running_mean, running_var, momentum, C, (cudaStream_t)stream);
+}
+int cspn_abn_forward_f32(float* x, const float* mean, const float* var, const float* weight, const float* bias, int N, int C, int S, float eps,
+                         int activation, float slope, void* stream)
+{
+    if (!abn_shape_ok(N, C, S, activation)) return CSPN_ERR_BAD_SHAPE;
+    if (!x || !mean || !var) return CSPN_ERR_NULL_POINTER;
+    call_stats().launches = 0;
+    return abn_forward(x, mean, var, weight, bias, N, C, S, eps, activation, slope, (cudaStream_t)stream);
+}
+int cspn_abn_bwd_reduce_f32(const float* z, const float* dz, const float* weight, const float* bias, int N, int C, int S, float eps, int activation,
+                            float slope, double* sums, void* ws, size_t ws_bytes, void* stream)
+{
+    if (!abn_shape_ok(N, C, S, activation)) return CSPN_ERR_BAD_SHAPE;
+    if (!z || !dz || !sums) return CSPN_ERR_NULL_POINTER;
+    if (!ws || ws_bytes < abn_workspace_bytes(C) || ((uintptr_t)ws & 7)) return CSPN_ERR_WORKSPACE;
+    call_stats().launches = 0;
+    return abn_bwd_reduce(z, dz, weight, bias, N, C, S, eps, activation, slope, sums, ws, (cudaStream_t)stream);
+}
+int cspn_abn_bwd_apply_f32(const float* z, const float* dz, float* dx, const float* var, const float* weight, const float* bias, const double* sums,
+                           double count_total, double count_local, float* dweight, float* dbias, int N, int C, int S, float eps, int activation,
+                           float slope, void* stream)
+{
+    if (!abn_shape_ok(N, C, S, activation) || !(count_total >= 1.0)) return CSPN_ERR_BAD_SHAPE;
+    if (!z || !dz || !var || (dweight && !weight)) return CSPN_ERR_NULL_POINTER;
+    call_stats().launches = 0;
+    return abn_bwd_apply(z, dz, dx, var, weight, bias, sums, count_total, count_local, dweight, dbias, N, C, S, eps, activation, slope, (cudaStream_t)stream);
+}
 size_t cspn_heads_workspace_bytes(void) { return heads_workspace_bytes(); }
 int cspn_heads_fwd_f32(const float* x, const float* w1, const float* w2, float* out1, float* out2, int B, int Cin, int h, int w, int H, int W, int n1, int n2,
                        void* stream)

@@ -123,6 +123,17 @@ template <typename T> int heads_forward(const T* x, const T* w1, const T* w2, T*
 template <typename T> int heads_backward(const T* x, const T* w1, const T* w2, const T* go1, const T* go2, T* gx, T* gw1, T* gw2, int n1, int n2, int B,
                                          int Cin, int h, int w, int H, int W, void* ws, cudaStream_t stream);
 
+// in-place activated batch normalisation (cspn_abn.cu): fp32, NCHW; act: 0 none, 1 leaky_relu, 2 elu
+size_t abn_workspace_bytes(int C);
+int abn_stats(const float* x, int N, int C, int S, double* sums, void* ws, cudaStream_t stream);
+int abn_finalize(const double* sums, double count, float* mean, float* var, float* running_mean, float* running_var, float momentum, int C, cudaStream_t stream);
+int abn_forward(float* x, const float* mean, const float* var, const float* weight, const float* bias, int N, int C, int S, float eps, int act, float slope,
+                cudaStream_t stream);
+int abn_bwd_reduce(const float* z, const float* dz, const float* weight, const float* bias, int N, int C, int S, float eps, int act, float slope, double* sums,
+                   void* ws, cudaStream_t stream);
+int abn_bwd_apply(const float* z, const float* dz, float* dx, const float* var, const float* weight, const float* bias, const double* sums, double count_total,
+                  double count_local, float* dweight, float* dbias, int N, int C, int S, float eps, int act, float slope, cudaStream_t stream);
+
 // legacy max-of-8 CSPN (cspn_legacy.cu): temporally blocked forward, 4 steps per launch
 size_t legacy_workspace(int B, int H, int W, int iters);
 template <typename T> int legacy_forward(const T* guidance, int64_t gbs, const T* depth, const T* sparse, T* out, int B, int H, int W, int iters,

@@ -176,6 +176,35 @@ CSPN_API int cspn_heads_bwd_f16(const void* x, const void* w1, const void* w2, c
                                 void* gx, void* gw1, void* gw2, int B, int Cin, int h, int w, int H, int W, int n1, int n2,
                                 void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- in-place activated batch normalisation ------------------------------------------------------------
+ * The reference's own native interface for this is network/libs/inplace_abn/src/lib_cffi.h / bn.h:
+ *   bn_mean_var_cuda (bn.cu:235-249)  -> cspn_abn_stats_f32 + cspn_abn_finalize_f32
+ *   bn_forward_cuda (:251-266) + leaky_relu_cuda / elu_cuda (:299-335)  -> cspn_abn_forward_f32 (one pass, in place)
+ *   leaky_relu_backward_cuda / elu_backward_cuda / elu_inv_cuda (:312-377) + bn_edz_eydz_cuda (:268-283)  -> cspn_abn_bwd_reduce_f32
+ *   bn_backard_cuda (:285-297)  -> cspn_abn_bwd_apply_f32
+ * called from functions.py:70-163 (InPlaceABN) and :166-297 (InPlaceABNSync).  fp32, x [N,C,S] contiguous (S = H*W).
+ * activation: 0 none, 1 leaky_relu(slope), 2 elu.  weight / bias may be NULL (affine=False): gamma = |weight| + eps, beta = bias.
+ * sums: DEVICE vector of 2*C doubles - {sum x, sum x^2} per channel for the statistics, {sum dz, sum y*dz} for the backward.
+ * The synchronised variant all-reduces (SUM) exactly this vector across ranks between the reduce and the finalize / apply call
+ * and passes count = N*S*world.  workspace: cspn_abn_workspace_bytes(C) bytes, 8-byte aligned.
+ *   cspn_abn_finalize_f32: mean, var (biased) from sums / count; running_mean / running_var (may be NULL) updated with momentum and
+ *     the n/(n-1) correction (functions.py:90-92).
+ *   cspn_abn_forward_f32: x <- act((x - mean) / sqrt(var + eps) * gamma + beta) IN PLACE.
+ *   cspn_abn_bwd_reduce_f32: z is the saved OUTPUT, dz its gradient; neither is modified (the activation is undone on the fly).
+ *   cspn_abn_bwd_apply_f32: dx (may alias dz; NULL = skip) = (dz' - edz - y*eydz) * gamma / sqrt(var + eps); sums == NULL is the
+ *     inference-mode backward (edz = eydz = 0); dweight / dbias (may be NULL) = sign(weight) * eydz * count_local, edz * count_local. */
+CSPN_API size_t cspn_abn_workspace_bytes(int C);
+CSPN_API int cspn_abn_stats_f32(const float* x, int N, int C, int S, double* sums, void* workspace, size_t workspace_bytes, void* stream);
+CSPN_API int cspn_abn_finalize_f32(const double* sums, double count, float* mean, float* var, float* running_mean, float* running_var,
+                                   float momentum, int C, void* stream);
+CSPN_API int cspn_abn_forward_f32(float* x, const float* mean, const float* var, const float* weight, const float* bias,
+                                  int N, int C, int S, float eps, int activation, float slope, void* stream);
+CSPN_API int cspn_abn_bwd_reduce_f32(const float* z, const float* dz, const float* weight, const float* bias, int N, int C, int S,
+                                     float eps, int activation, float slope, double* sums, void* workspace, size_t workspace_bytes, void* stream);
+CSPN_API int cspn_abn_bwd_apply_f32(const float* z, const float* dz, float* dx, const float* var, const float* weight, const float* bias,
+                                    const double* sums, double count_total, double count_local, float* dweight, float* dbias,
+                                    int N, int C, int S, float eps, int activation, float slope, void* stream);
+
 /* ---- legacy max-of-8 CSPN ---------------------------------------------------------------------------
  * network/libs/post_process/CSPN.py:19-56, AffinityPropagate().forward(guidance, blur_depth, sparse_depth), and :132-164,
  * AffinityPropagate_prediction().forward(guidance, blur_depth) (sparse == NULL).  Per step and gate k = 0..7 (|guidance[:,k]|,
