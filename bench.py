@@ -649,6 +649,27 @@ def neighbour_rows(dev):
         ms_m = _event_ms(lambda: criteria.evaluate_device(pred, target), 50, dev)
     rows["masked_l1_fwd_bwd_and_metrics_nyu_b8"] = {"loss_fwd_bwd_ms": ms_l, "metrics_ms": ms_m, "launches": "1 + 1, 1",
                                                     "what": "eager Python calls: the kernels stream 4.4 MB, the time is launch + autograd overhead"}
+    # in-place activated batch norm (network/libs/inplace_abn) on the decoder's last 64-channel activation, training mode
+    from cspn_monodepth_b200 import abn
+    bn = abn.InPlaceABN(cin).to(dev)
+    bn_ref = torch.nn.Sequential(torch.nn.BatchNorm2d(cin), torch.nn.LeakyReLU(0.01)).to(dev)
+    act_in = torch.randn(b, cin, h, w, generator=gen).to(dev).requires_grad_(True)
+    gz = torch.randn(b, cin, h, w, generator=gen).to(dev)
+    n_el = b * cin * h * w
+
+    def abn_step(mod):
+        def run():
+            act_in.grad = None
+            mod(act_in * 1.0).backward(gz)
+        return run
+    with torch.no_grad():
+        buf = torch.empty_like(act_in)
+        ms_f = _event_ms(lambda: bn(buf.copy_(act_in)), 50, dev) - _event_ms(lambda: buf.copy_(act_in), 50, dev)
+    ms_fb, ms_fb_ref = _event_ms(abn_step(bn), 30, dev), _event_ms(abn_step(bn_ref), 30, dev)
+    rows["inplace_abn_b8x64x114x152_f32"] = {"fwd_ms": ms_f, "fwd_roofline_frac": 12.0 * n_el / (ms_f * 1e-3) / 1e9 / hbm_peak()[0],
+                                             "fwd_bwd_ms": ms_fb, "torch_batchnorm_leakyrelu_fwd_bwd_ms": ms_fb_ref, "launches": "3 + 1 forward, 2 + 1 backward",
+                                             "what": "InPlaceABN(64) training step on 8x64x114x152 (35.5 MB): forward = 12 B/element (statistics read + "
+                                                     "normalise in place), backward = 20 B/element; both timings include the x*1.0 copy that feeds the module"}
     # the tail of unet_cspn_nyu.ResNet.forward (:383-386) + criterion, forward + backward
     prop = cspn_new.AffinityPropagate(24, 3)
 
@@ -755,6 +776,9 @@ def main():
         from cspn_monodepth_b200 import _lib
         plan = _lib.forward_plan(cfg["B"], 1, cfg["H"], cfg["W"], cfg["iters"], cfg["ksize"], cfg["mode"])
         kernel = {1: "cspn::fused3x3_kernel<float,10,8,CSPN_new> (single 64x80 tile per CTA)", 2: "cspn::dual3x3_kernel<float,10,CSPN_new> (two 64x40 tiles per CTA)"}.get(plan["kernel"], "?")
+        if plan.get("transport"):
+            kernel += {"cluster": ", hardware clusters (DSMEM halo ring)", "stream": ", stream transport (halo ring through global inboxes)",
+                       "hybrid": ", hybrid transport (row clusters: DSMEM left / right, global inboxes up / down)"}[plan["transport"]]
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(cfg, nsets), "gpu_launches": launches * args.steps,

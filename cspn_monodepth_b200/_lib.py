@@ -108,7 +108,10 @@ def forward_plan(b: int, c: int, h: int, w: int, iters: int, ksize: int = 3, mod
     buf = (_c_int * 10)()
     check(load().cspn_fwd_plan(b, c, h, w, iters, ksize, mode, buf))
     keys = ("kernel", "rows_per_warp", "cx", "cy", "ntx", "nty", "ctas", "rounds", "units_per_class", "units")
-    return dict(zip(keys, list(buf)))
+    plan = dict(zip(keys, list(buf)))
+    if plan["kernel"] == KERNEL_SINGLE:                  # the second word is the halo transport (CSPN_TRANSPORT_*), not a tile height
+        plan["transport"] = ("cluster", "stream", "hybrid")[plan.pop("rows_per_warp")]
+    return plan
 
 
 _torch_ext = None

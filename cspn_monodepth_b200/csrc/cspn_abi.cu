@@ -434,7 +434,7 @@ int cspn_fwd_plan(int B, int C, int H, int W, int iters, int ksize, int mode, in
     if (B < 1 || C < 1 || H < 1 || W < 1 || iters < 1) return CSPN_ERR_BAD_SHAPE;
     if (use_fused(B, C, H, W, iters, ksize, mode, nullptr)) {
         if (dual_supported(B, C, H, W, iters, ksize, mode)) { plan10[0] = CSPN_KERNEL_DUAL; dual_describe(B, C, H, W, iters, plan10 + 1); }
-        else plan10[0] = CSPN_KERNEL_SINGLE;
+        else { plan10[0] = CSPN_KERNEL_SINGLE; single_describe(B, C, H, W, iters, plan10 + 1); }
     } else if (use_blocked(B, C, H, W, iters, ksize, mode)) plan10[0] = CSPN_KERNEL_BLOCKED;
     else plan10[0] = CSPN_KERNEL_GENERIC;
     return CSPN_OK;

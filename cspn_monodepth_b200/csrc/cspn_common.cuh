@@ -84,7 +84,7 @@ template <typename T> int generic_backward(const BwdArgs<T>& a, const TapTable& 
 constexpr long kMaxGlobalExchangeCtas = 1l << 20;  // upper bound on the tiles of a streamed problem (one inbox each)
 // Cluster shape (cx x cy CTAs) and grid of cluster tiles (ntx x nty per image) covering an image.  stream: the image is
 // one virtual cluster walked by a persistent grid with the halo exchange in global memory (no hardware cluster).
-struct Tiling { int cx, cy, ntx, nty, stepx, stepy, ew, eh; long ctas; bool ok; bool stream; };
+struct Tiling { int cx, cy, ntx, nty, stepx, stepy, ew, eh; long ctas; bool ok; bool stream; bool hyb; };
 // What the GPU holds at once for one kernel configuration: sms = CTA slots of the whole GPU (SMs x resident CTAs per
 // SM), clusters[n] = co-resident hardware clusters of n CTAs.
 struct Capacity { int sms; int clusters[17]; };
@@ -99,6 +99,7 @@ constexpr int kDualFallback = -1000;   // internal: "not this kernel" (unaligned
 bool dual_supported(int B, int C, int H, int W, int iters, int ksize, int mode);
 size_t dual_workspace(int B, int C, int H, int W, int iters);
 void dual_describe(int B, int C, int H, int W, int iters, int* out9);
+void single_describe(int B, int C, int H, int W, int iters, int* out9);   // {transport, cx, cy, ntx, nty, CTAs per plane, 0, 0, 0}
 template <typename T> int dual_forward(const FwdArgs<T>& a);
 
 // temporally blocked forward for the 5x5 variant (cspn_blocked5x5.cu): 4 steps per launch, weights in registers

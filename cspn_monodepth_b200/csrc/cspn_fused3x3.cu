@@ -17,7 +17,7 @@ constexpr int kTHBig = kNW * kPFwd;
 
 Tiling plan_forward(int B, int C, int H, int W, int iters)
 {
-    return choose_tiling(H, W, iters, kTHBig, (long)B * C, capacity<kPFwd, kNW, false>());
+    return choose_tiling(H, W, iters, kTHBig, (long)B * C, capacity<kPFwd, kNW, false>(), true);
 }
 }  // namespace
 
@@ -31,6 +31,15 @@ static bool single_ok(int B, int C, int H, int W, int iters)
 
 bool fused_single_possible(int B, int C, int H, int W, int iters) { return single_ok(B, C, H, W, iters); }
 
+void single_describe(int B, int C, int H, int W, int iters, int* out9)
+{
+    for (int i = 0; i < 9; ++i) out9[i] = 0;
+    if (!single_ok(B, C, H, W, iters)) return;
+    const Tiling tl = plan_forward(B, C, H, W, iters);
+    out9[0] = tl.hyb ? CSPN_TRANSPORT_HYBRID : (tl.stream ? CSPN_TRANSPORT_STREAM : CSPN_TRANSPORT_CLUSTER);
+    out9[1] = tl.cx; out9[2] = tl.cy; out9[3] = tl.ntx; out9[4] = tl.nty; out9[5] = (int)tl.ctas;
+}
+
 bool fused_supported(int B, int C, int H, int W, int iters, int ksize, int mode)
 {
     if (ksize != 3 || iters < 1 || B < 1) return false;
@@ -41,7 +50,7 @@ static size_t single_workspace(int B, int C, int H, int W, int iters)
 {
     if (!single_ok(B, C, H, W, iters)) return 0;
     const Tiling tl = plan_forward(B, C, H, W, iters);
-    if (!tl.stream) return 0;
+    if (!tl.stream && !tl.hyb) return 0;
     return kStatusBytes + (size_t)(tl.ctas * (long)B * C) * inbox_bytes<kTHBig>();     // status word + inboxes of the global-memory exchange, one per tile
 }
 

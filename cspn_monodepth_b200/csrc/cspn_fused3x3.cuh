@@ -275,7 +275,7 @@ template <int TH> struct BwdTiles {
 // One CTA tile from prologue to epilogue.  (bx, by, bz) = position of the tile in the (gdx, gdy, planes) grid of CTA
 // tiles - the launch grid itself for hardware clusters, the tile counter of the persistent loop for the global-memory
 // exchange; use = how many tiles this CTA has processed before (phase parity of the re-used TMA barriers).
-template <typename T, int P, int NW, int MODE, bool TMA, bool GLB, bool BWD>
+template <typename T, int P, int NW, int MODE, bool TMA, bool GLB, bool BWD, bool HYB = false>
 __device__ __forceinline__ void fused_tile(const FusedParams<T>& p, const CUtensorMap* gmap, unsigned char* smem_raw,
                                            const uint32_t bx, const uint32_t by, const uint32_t bz, const uint32_t gdx, const uint32_t gdy, const uint32_t use)
 {
@@ -316,6 +316,12 @@ __device__ __forceinline__ void fused_tile(const FusedParams<T>& p, const CUtens
     }
     TRACE(1);
     const bool hw_cluster = multi && !GLB;
+    // HYB (forward only): hardware clusters of (cx, 1) CTAs - one per tile row of an image.  Left / right neighbours talk through
+    // DSMEM like any cluster, the tile rows above / below (other clusters) through the global-memory inboxes of the stream
+    // transport; the row rims leave straight from the sweep, as soon as they are final, so that their L2 trip overlaps the rest
+    // of the step.  Every cluster of the launch must be resident at once (planner: clusters <= co-resident clusters of cx).
+    static_assert(!HYB || (!GLB && !BWD), "the hybrid transport is a forward cluster variant");
+    constexpr bool GLBX = GLB || HYB;                    // some messages travel through the global inboxes
 
     const T* db = p.depth + dplane * hw;
     const T* sb = p.sparse ? p.sparse + ((size_t)b * p.sparse_channels + (p.sparse_channels == 1 ? 0 : ch)) * hw : nullptr;
@@ -479,13 +485,14 @@ __device__ __forceinline__ void fused_tile(const FusedParams<T>& p, const CUtens
     const int lx0 = has_left ? 1 : 0, lx1 = has_right ? 30 : 31;
     const int ry0 = has_up ? kHaloY : 0, ry1 = has_down ? TH - 1 - kHaloY : TH - 1;
     const bool lane_auth = lane >= lx0 && lane <= lx1;
-    const uint32_t my_rank = (uint32_t)(ccx + ccy * p.cx);      // == %cluster_ctarank for a (cx, cy, 1) cluster
+    const uint32_t my_rank = HYB ? (uint32_t)ccx : (uint32_t)(ccx + ccy * p.cx);      // == %cluster_ctarank for a (cx, cy, 1) [HYB: (cx, 1, 1)] cluster
     // bytes this CTA receives per refresh: 8 per row from the left / right neighbour, whole rows (all 32 lanes; halo
     // lanes of a row are overridden by the column boxes) from above / below, 2x8 from each diagonal neighbour
-    const uint32_t expect_bytes = 8u * (uint32_t)(((has_left ? 1 : 0) + (has_right ? 1 : 0)) * (ry1 - ry0 + 1) +
-                                                  ((has_up ? 1 : 0) + (has_down ? 1 : 0)) * kHaloY * 32 +
-                                                  kHaloY * (((has_up && has_left) ? 1 : 0) + ((has_up && has_right) ? 1 : 0) +
-                                                            ((has_down && has_left) ? 1 : 0) + ((has_down && has_right) ? 1 : 0)));
+    const uint32_t expect_bytes = HYB ? 8u * (uint32_t)(((has_left ? 1 : 0) + (has_right ? 1 : 0)) * (ry1 - ry0 + 1))      // rows and corners arrive through global memory
+                                      : 8u * (uint32_t)(((has_left ? 1 : 0) + (has_right ? 1 : 0)) * (ry1 - ry0 + 1) +
+                                                        ((has_up ? 1 : 0) + (has_down ? 1 : 0)) * kHaloY * 32 +
+                                                        kHaloY * (((has_up && has_left) ? 1 : 0) + ((has_up && has_right) ? 1 : 0) +
+                                                                  ((has_down && has_left) ? 1 : 0) + ((has_down && has_right) ? 1 : 0)));
     const uint32_t sm_base = smem_u32(&sm);
     using SmemT = Smem<NW, P>;
     using IG = InboxGeom<TH>;
@@ -520,6 +527,8 @@ __device__ __forceinline__ void fused_tile(const FusedParams<T>& p, const CUtens
         if (lane < 2 * P) {
             side = lane / P; srow = drow = ty0 + lane % P;
             if (srow < ry0 || srow > ry1) side = -1;
+        } else if (HYB) {
+            // corner messages leave with the row rims (ship_row)
         } else if (lane < 2 * P + 2 * kHaloY) {
             if (warp == 0 && has_up) { side = (lane - 2 * P) / kHaloY; const int h = (lane - 2 * P) % kHaloY; srow = kHaloY + h; drow = TH - kHaloY + h; dcy = -1; }
         } else if (lane < 2 * P + 4 * kHaloY) {
@@ -551,6 +560,31 @@ __device__ __forceinline__ void fused_tile(const FusedParams<T>& p, const CUtens
         if (warp < NW - 1) bot = *reinterpret_cast<const u64*>(&sm.rowbuf[par][warp + 1][0][2 * lane]);
     };
 
+    // GLB exchange: this warp's slots of the global inbox.  Lanes 0..P+1: left column rows ty0-1..ty0+P, lanes
+    // 16..16+P+1: right column; top / bottom warp: both halo rows, one slot per lane.
+    struct Polled { uint4 c, r0, r1; };
+    const int poll_sd = lane >> 4, poll_row = warp * P - 1 + (lane & 15);
+    // HYB: the column boxes are filled through DSMEM except for their halo rows (corner messages from the clusters above / below)
+    const bool poll_want = (lane & 15) < P + 2 && poll_row >= 0 && poll_row < TH && (poll_sd == 0 ? has_left : has_right) &&
+                           (!HYB || poll_row < ry0 || poll_row > ry1);
+    const bool poll_r0 = has_up && warp == 0, poll_r1 = has_down && warp == NW - 1;
+    // One read of the slots of refresh epoch e.  Issued BEFORE the intra-CTA row exchange of the step so that the L2
+    // round trip overlaps that barrier; take_refresh only re-reads what was not current yet.
+    auto poll = [&](int e) {
+        const uint32_t tag = p.tag_base + (uint32_t)e;
+        const int rpar = e & 1;
+        Polled q;
+        q.c = make_uint4(0, tag, 0, tag); q.r0 = q.c; q.r1 = q.c;
+        if (GLBX) {
+            const uint4* box = p.inbox + (size_t)my_blk * IG::size;
+            if (poll_want) q.c = ld_ll(box + rpar * IG::col_par + poll_sd * IG::col_side + poll_row);
+            if (poll_r0 || poll_r1) {
+                const uint4* rslot = box + IG::row_base + rpar * IG::row_par + (poll_r1 ? IG::row_side : 0u) + lane;
+                q.r0 = ld_ll(rslot); q.r1 = ld_ll(rslot + 32);
+            }
+        }
+        return q;
+    };
     // Ship the halo ring of refresh parity rpar to the neighbours: the warp's rim columns were staged into
     // sm.colstage by lanes 1 / 30 during the sweep; now lane m sends message m (one 8-byte st.async each, a single
     // warp-wide instruction), rim rows go out directly from all 32 lanes of the top / bottom warp.
@@ -565,6 +599,7 @@ __device__ __forceinline__ void fused_tile(const FusedParams<T>& p, const CUtens
             else st_async_b64(msg_dst + rpar * kColPar, v, msg_bar + 8u * rpar);
         }
         TRACE(91);
+        if (HYB) return;                                                             // the row rims left during the sweep (ship_row)
         if (has_up && warp == 0) {                                                   // warp-uniform
             // my tile rows kHaloY .. 2*kHaloY-1 are the upper neighbour's bottom halo rows
             if (GLB) {
@@ -591,6 +626,34 @@ __device__ __forceinline__ void fused_tile(const FusedParams<T>& p, const CUtens
             }
         }
         TRACE(92);
+    };
+
+    // HYB: tile row i of this warp just became final inside the sweep; if it is a rim row of the tile, it goes to the inbox of the
+    // tile above / below right away (i is a compile-time constant at every call site, the warp tests are uniform).
+    const bool ship_up = HYB && has_up && warp == 0, ship_down = HYB && has_down && warp == NW - 1;
+    static_assert(!HYB || NW >= 2, "top and bottom rim rows must live in different warps");
+    // destinations fixed for the whole loop (parity 0): this lane's slot of the row box of the tile above / below, and - lanes 1 / 30 -
+    // of the column box of the diagonal neighbour (the rim columns of the same rows are the corners of its ring)
+    uint4* row_dst = nullptr;
+    uint4* cor_dst = nullptr;
+    if (ship_up || ship_down) {
+        const uint32_t nb = ship_up ? my_blk - gdx : my_blk + gdx;
+        row_dst = p.inbox + (size_t)nb * IG::size + IG::row_base + (ship_up ? IG::row_side : 0u) + lane;
+        if (push_l) cor_dst = p.inbox + (size_t)(nb - 1) * IG::size + IG::col_side + (ship_up ? TH - kHaloY : 0);
+        if (push_r) cor_dst = p.inbox + (size_t)(nb + 1) * IG::size + (ship_up ? TH - kHaloY : 0);
+    }
+    auto ship_row = [&](int i, u64 a, int rpar, uint32_t tag) {
+        const bool top = i >= kHaloY && i < 2 * kHaloY, btm = i >= P - 2 * kHaloY && i < P - kHaloY;      // compile-time at every call site
+        if (!top && !btm) return;
+        if (top && btm) {                                      // short strips: the same row index is a top rim row in warp 0 and a bottom one in warp NW-1
+            const int h = ship_up ? i - kHaloY : i - (P - 2 * kHaloY);
+            if (row_dst) st_ll(row_dst + rpar * IG::row_par + h * 32, a, tag);
+            if (cor_dst) st_ll(cor_dst + rpar * IG::col_par + h, a, tag);
+        } else if (top ? ship_up : ship_down) {
+            const int h = top ? i - kHaloY : i - (P - 2 * kHaloY);
+            st_ll(row_dst + rpar * IG::row_par + h * 32, a, tag);
+            if (cor_dst) st_ll(cor_dst + rpar * IG::col_par + h, a, tag);
+        }
     };
 
     // One step, r'(p) = c(p) + sum_j n'_j(p) * r(p + o_j), organised by SOURCE row: row r's three pixel pairs
@@ -634,6 +697,7 @@ __device__ __forceinline__ void fused_tile(const FusedParams<T>& p, const CUtens
                 x0 = fmaf(lo_of(nw[i][7]), hi, x0);  x1 = fmaf(hi_of(nw[i][7]), rr, x1);
                 const u64 a = pk(x0, x1);
                 A[i] = a;
+                if (PUSH && HYB) ship_row(i, a, rpar, tag);
                 if (PUSH) {
                     const int ty = warp * P + i;
                     if (push_l) sm.colstage[rpar][0][ty] = a;
@@ -669,6 +733,7 @@ __device__ __forceinline__ void fused_tile(const FusedParams<T>& p, const CUtens
                 a = fma2(nw[i][6], src, a);
                 a = fma2(nw[i][7], s2, a);
                 A[i] = a;
+                if (PUSH && HYB) ship_row(i, a, rpar, tag);
                 if (PUSH) {
                     // stage the rim values locally (predicated stores, no branches); shipped in bulk after the sweep
                     const int ty = warp * P + i;
@@ -682,32 +747,12 @@ __device__ __forceinline__ void fused_tile(const FusedParams<T>& p, const CUtens
 
     // Take the refreshed halo ring of refresh epoch e (pushed by the neighbours during their previous step).
     bool poisoned = false;
-    // GLB exchange: this warp's slots of the global inbox.  Lanes 0..P+1: left column rows ty0-1..ty0+P, lanes
-    // 16..16+P+1: right column; top / bottom warp: both halo rows, one slot per lane.
-    struct Polled { uint4 c, r0, r1; };
-    const int poll_sd = lane >> 4, poll_row = warp * P - 1 + (lane & 15);
-    const bool poll_want = (lane & 15) < P + 2 && poll_row >= 0 && poll_row < TH && (poll_sd == 0 ? has_left : has_right);
-    const bool poll_r0 = has_up && warp == 0, poll_r1 = has_down && warp == NW - 1;
-    // One read of the slots of refresh epoch e.  Issued BEFORE the intra-CTA row exchange of the step so that the L2
-    // round trip overlaps that barrier; take_refresh only re-reads what was not current yet.
-    auto poll = [&](int e) {
-        const uint32_t tag = p.tag_base + (uint32_t)e;
-        const int rpar = e & 1;
-        Polled q;
-        q.c = make_uint4(0, tag, 0, tag); q.r0 = q.c; q.r1 = q.c;
-        if (GLB) {
-            const uint4* box = p.inbox + (size_t)my_blk * IG::size;
-            if (poll_want) q.c = ld_ll(box + rpar * IG::col_par + poll_sd * IG::col_side + poll_row);
-            if (poll_r0 || poll_r1) {
-                const uint4* rslot = box + IG::row_base + rpar * IG::row_par + (poll_r1 ? IG::row_side : 0u) + lane;
-                q.r0 = ld_ll(rslot); q.r1 = ld_ll(rslot + 32);
-            }
-        }
-        return q;
-    };
+#ifdef CSPN_TRACE
+    int repolls = 0;
+#endif
     auto take_refresh = [&](int e, Polled q, u64& top, u64& bot) {
         const int rpar = e & 1;
-        if (GLB) {
+        if (GLBX) {
             // wait until every tag is current, then drop the payload into the same shared-memory boxes the DSMEM path fills
             const uint32_t tag = p.tag_base + (uint32_t)e;
             const int sd = poll_sd, row = poll_row;
@@ -715,6 +760,9 @@ __device__ __forceinline__ void fused_tile(const FusedParams<T>& p, const CUtens
             for (int spin = 0; !poisoned; ++spin) {
                 const bool ok = q.c.y == tag && q.c.w == tag && q.r0.y == tag && q.r0.w == tag && q.r1.y == tag && q.r1.w == tag;
                 if (__all_sync(0xffffffffu, ok)) break;
+#ifdef CSPN_TRACE
+                ++repolls;
+#endif
                 if (spin > (1 << 21)) { poisoned = true; break; }     // neighbours never showed up (grid not co-resident?): fail loudly, do not hang
                 q = poll(e);
             }
@@ -730,9 +778,10 @@ __device__ __forceinline__ void fused_tile(const FusedParams<T>& p, const CUtens
                 *reinterpret_cast<uint2*>(&sm.rowbox[rpar][wr1 ? 1 : 0][1][2 * lane]) = make_uint2(r1.x, r1.z);
             }
             __syncwarp();
-        } else {
-            mbar_wait(sm_base + kHaloBar + 8u * rpar, (uint32_t)(((e - 1) >> 1) & 1));
         }
+        TRACE(93);
+        if (!GLB) mbar_wait(sm_base + kHaloBar + 8u * rpar, (uint32_t)(((e - 1) >> 1) & 1));
+        TRACE(94);
         if (has_up && warp == 0) {
 #pragma unroll
             for (int h = 0; h < kHaloY; ++h) A[h] = *reinterpret_cast<const u64*>(&sm.rowbox[rpar][0][h][2 * lane]);
@@ -780,7 +829,7 @@ __device__ __forceinline__ void fused_tile(const FusedParams<T>& p, const CUtens
         u64 top, bot;
         if (t < 24) TRACE(16 + 3 * t);
         Polled pq{};
-        if (GLB && multi && t > 0) pq = poll(e);
+        if (GLBX && multi && t > 0) pq = poll(e);
         exchange_rows(0, top, bot);
         if (t < 24) TRACE(17 + 3 * t);
         if (multi && t > 0) take_refresh(e, pq, top, bot);
@@ -805,6 +854,9 @@ __device__ __forceinline__ void fused_tile(const FusedParams<T>& p, const CUtens
         }
     }
     TRACE(14);
+#ifdef CSPN_TRACE
+    if (g_trace && lane == 0) g_trace[((size_t)(blockIdx.z * gridDim.y * gridDim.x + blockIdx.y * gridDim.x + blockIdx.x) * (blockDim.x >> 5) + warp) * kTraceSlots + 95] = repolls;
+#endif
 
     // region of this cluster tile whose results are exact (not inside the decaying margin of a tile edge that is
     // not an image border); every image pixel is inside exactly one such region
@@ -814,7 +866,7 @@ __device__ __forceinline__ void fused_tile(const FusedParams<T>& p, const CUtens
     const int vy1 = tiy == p.nty - 1 ? H : tiy * p.stepy + p.eh - p.margin;
 
     if constexpr (!BWD) {
-        if (GLB && multi) {
+        if (GLBX && multi) {
             // every message addressed to this CTA has been consumed: leave the inbox clean for the next launch / graph replay
             __syncthreads();
             uint4* box = p.inbox + (size_t)my_blk * IG::size;
@@ -1106,7 +1158,7 @@ __device__ __forceinline__ void fused_tile(const FusedParams<T>& p, const CUtens
             }
         }
     }
-    if (GLB && poisoned && p.status && lane == 0) *p.status = 1;
+    if (GLBX && poisoned && p.status && lane == 0) *p.status = 1;
     TRACE(15);
 }
 
@@ -1117,7 +1169,7 @@ __device__ __forceinline__ void fused_tile(const FusedParams<T>& p, const CUtens
 // tiles only ever wait for tiles of their own image at most cx + 1 positions away: with more CTAs than that, the
 // CTA owning a larger-numbered neighbour is at worst busy with a tile that precedes every tile waiting for it, so
 // the wavefront always advances (the spin in take_refresh is bounded regardless).
-template <typename T, int P, int NW, int MODE, bool TMA, bool GLB, bool BWD>
+template <typename T, int P, int NW, int MODE, bool TMA, bool GLB, bool BWD, bool HYB = false>
 __global__ void __launch_bounds__(NW * 32, (NW <= 5 ? 2 : 1))
 fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant__ CUtensorMap gmap)
 {
@@ -1131,11 +1183,11 @@ fused3x3_kernel(const __grid_constant__ FusedParams<T> p, const __grid_constant_
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (GLB && blockIdx.x == 0 && threadIdx.x == 0 && p.status) *p.status = 0;     // a timeout (2^21 polls later at the earliest) sets it to 1
+    if ((GLB || HYB) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0 && p.status) *p.status = 0;     // a timeout (2^21 polls later at the earliest) sets it to 1
     if (!GLB) {
         // "my barriers exist": neighbours may only push into this CTA after everyone passed the matching wait
         if (p.cx * p.cy > 1) cluster_arrive();
-        fused_tile<T, P, NW, MODE, TMA, GLB, BWD>(p, &gmap, smem_raw, blockIdx.x, blockIdx.y, blockIdx.z, gridDim.x, gridDim.y, 0u);
+        fused_tile<T, P, NW, MODE, TMA, GLB, BWD, HYB>(p, &gmap, smem_raw, blockIdx.x, blockIdx.y, blockIdx.z, gridDim.x, gridDim.y, 0u);
     } else {
         const uint32_t per_image = (uint32_t)(p.cx * p.cy);
         uint32_t use = 0u;
@@ -1186,7 +1238,11 @@ inline Capacity default_capacity(int ctas_per_sm = 1)
 
 inline int exchange_override()
 {
-    static const int force = [] { const char* v = getenv("CSPN_EXCHANGE"); return !v ? 0 : (!strcmp(v, "dsmem") ? 1 : (!strcmp(v, "global") ? 2 : 0)); }();   // debugging knob
+    // debugging knob: dsmem = hardware clusters only, global = stream wherever it is possible, hybrid = row clusters wherever possible
+    static const int force = [] {
+        const char* v = getenv("CSPN_EXCHANGE");
+        return !v ? 0 : (!strcmp(v, "dsmem") ? 1 : (!strcmp(v, "global") ? 2 : (!strcmp(v, "hybrid") ? 3 : 0)));
+    }();
     return force;
 }
 
@@ -1195,7 +1251,10 @@ inline int exchange_override()
 //    CTAs with decaying margins between them; time ~ ceil(clusters / co-resident clusters of that size);
 //  * stream (tl.stream): every image is one virtual cluster of cx x cy tiles without margins, halo exchange through
 //    global memory, a persistent grid of one CTA per SM slot walks the tiles as a wavefront; time ~ tiles / slots.
-inline Tiling choose_tiling(int H, int W, int iters, int th, long planes, const Capacity& cap)
+//  * hybrid (tl.hyb, forward only): the stream tiling, but every tile ROW of an image is a hardware cluster of (cx, 1) CTAs:
+//    left / right rims through DSMEM, the rows above / below through the global inboxes, shipped from inside the sweep.  One CTA
+//    per tile, every cluster resident at once (cy * planes <= co-resident clusters of cx CTAs).
+inline Tiling choose_tiling(int H, int W, int iters, int th, long planes, const Capacity& cap, bool allow_hyb = false)
 {
     const int step_y = th - 2 * kHaloY;
     Tiling best{}; best.ok = false; best.ctas = 0; best.stream = false;
@@ -1244,6 +1303,14 @@ inline Tiling choose_tiling(int H, int W, int iters, int th, long planes, const 
             double cost = (double)((planes + groups - 1) / groups);
             if (exchange_override() == 2) cost = 0.0;
             consider(t, cost);
+        }
+        // hybrid (opt-in, CSPN_EXCHANGE=hybrid): one round by construction.  Measured 27.6-28.1 vs 28.3 us on the headline and 30.0 vs
+        // 32.3 us in mode OURS: not enough to make a transport the default that needs every cluster resident at once
+        // without a hardware guarantee for it
+        if (allow_hyb && exchange_override() == 3 && t.cx >= 2 && t.cx <= 16 && t.cy >= 2 && planes <= 65535 &&
+            t.cy * planes <= (long)cap.clusters[t.cx] && total <= kMaxGlobalExchangeCtas) {
+            Tiling h = t; h.stream = false; h.hyb = true;
+            consider(h, 0.0);
         }
     }
     return best;
@@ -1295,10 +1362,10 @@ constexpr size_t fused_smem_bytes()
     return sizeof(Smem<NW, P>) + dyn + (BWD ? BwdTiles<NW * P>::stash_bytes : 0);
 }
 
-template <typename T, int P, int NW, int MODE, bool TMA, bool GLB, bool BWD>
+template <typename T, int P, int NW, int MODE, bool TMA, bool GLB, bool BWD, bool HYB = false>
 int launch_variant(const FusedParams<T>& p, const CUtensorMap& map, const Tiling& tl, int planes, long grid_ctas, cudaStream_t stream)
 {
-    auto kern = fused3x3_kernel<T, P, NW, MODE, TMA, GLB, BWD>;
+    auto kern = fused3x3_kernel<T, P, NW, MODE, TMA, GLB, BWD, HYB>;
     constexpr size_t smem = fused_smem_bytes<T, P, NW, MODE, TMA, BWD>();
     static_assert(smem * (NW <= 5 ? 2 : 1) <= 227 * 1024, "shared memory budget of one SM exceeded");
     // the two opt-ins are per device and last for the life of the context: set them once per device, not on every launch
@@ -1314,21 +1381,35 @@ int launch_variant(const FusedParams<T>& p, const CUtensorMap& map, const Tiling
         configured.fetch_or(bit, std::memory_order_release);
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = GLB ? dim3((unsigned)grid_ctas) : dim3((unsigned)(tl.ntx * tl.cx), (unsigned)(tl.nty * tl.cy), (unsigned)planes);
+    cfg.gridDim = GLB ? dim3((unsigned)grid_ctas) : dim3((unsigned)(tl.ntx * tl.cx), (unsigned)(tl.nty * tl.cy), (unsigned)planes);   // HYB: ntx = nty = 1
     cfg.blockDim = dim3(NW * 32);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
+    cfg.attrs = at; cfg.numAttrs = 1;
     if (GLB) {
         // neighbours talk through global memory and spin on it: every CTA of the grid must be resident
         at[0].id = cudaLaunchAttributeCooperative;
         at[0].val.cooperative = 1;
     } else {
         at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = (unsigned)tl.cx; at[0].val.clusterDim.y = (unsigned)tl.cy; at[0].val.clusterDim.z = 1;
+        at[0].val.clusterDim.x = (unsigned)tl.cx; at[0].val.clusterDim.y = HYB ? 1u : (unsigned)tl.cy; at[0].val.clusterDim.z = 1;
+        if (HYB) {
+            // the clusters of an image spin on each other through global memory: ask for a co-resident (cooperative) grid as
+            // well; the planner only offers this transport when the occupancy query says every cluster fits at once
+            at[1].id = cudaLaunchAttributeCooperative;
+            at[1].val.cooperative = 1;
+            cfg.numAttrs = 2;
+        }
     }
-    cfg.attrs = at; cfg.numAttrs = 1;
     e = cudaLaunchKernelEx(&cfg, kern, p, map);
+    if (HYB && e != cudaSuccess) {
+        // cluster + cooperative refused by this driver: plain cluster launch (co-residency rests on the occupancy query; a
+        // neighbour that never shows up ends in the bounded spin and CSPN_ERR_EXCHANGE_TIMEOUT, not in a hang)
+        cudaGetLastError();
+        cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, kern, p, map);
+    }
     if (e != cudaSuccess) return (int)e;
     ++call_stats().launches;
     return 0;
@@ -1402,7 +1483,7 @@ int launch(FusedParams<T> p, const Tiling& tl, int B, void* inbox, size_t inbox_
     // in global memory (one per tile), walked by a persistent grid of at most one CTA per SM slot.
     const bool glb = tl.stream;
     long grid_ctas = 0;
-    if (glb) {
+    if (glb || tl.hyb) {
         const long total = tl.ctas * planes;
         if (!inbox || inbox_avail < kStatusBytes + (size_t)total * inbox_bytes<TH>()) return CSPN_ERR_WORKSPACE;
         p.status = (int*)inbox;                                       // first word of the scratch: exchange-timeout flag
@@ -1416,6 +1497,9 @@ int launch(FusedParams<T> p, const Tiling& tl, int B, void* inbox, size_t inbox_
     alignas(64) CUtensorMap map;
     memset(&map, 0, sizeof map);
     const bool tma = make_guidance_map<T, TH, MODE>(p.g, p.gbs, B, p.H, p.W, &map);      // false: unaligned guidance, plain-load prologue
+    if constexpr (!BWD) {
+        if (tl.hyb) return tma ? launch_variant<T, P, NW, MODE, true, false, false, true>(p, map, tl, planes, 0, stream) : launch_variant<T, P, NW, MODE, false, false, false, true>(p, map, tl, planes, 0, stream);
+    }
     if (glb) return tma ? launch_variant<T, P, NW, MODE, true, true, BWD>(p, map, tl, planes, grid_ctas, stream) : launch_variant<T, P, NW, MODE, false, true, BWD>(p, map, tl, planes, grid_ctas, stream);
     return tma ? launch_variant<T, P, NW, MODE, true, false, BWD>(p, map, tl, planes, 0, stream) : launch_variant<T, P, NW, MODE, false, false, BWD>(p, map, tl, planes, 0, stream);
 }

@@ -101,7 +101,11 @@ CSPN_API size_t cspn_bwd_workspace_bytes(int B, int C, int H, int W, int iters, 
 /* Diagnostics: which forward kernel the planner picks for a problem on the current device (what the launch will use
  * for TMA-addressable guidance).  plan10[0] = CSPN_KERNEL_*; for CSPN_KERNEL_DUAL the rest is {rows per warp P (tile =
  * 64 x 8P pixels), tiles per unit cx, cy, units per image plane ntx, nty, CTAs, rounds, units per class and round,
- * units}; zeros otherwise.  Not needed to call the operators. */
+ * units}; for CSPN_KERNEL_SINGLE {halo transport CSPN_TRANSPORT_*, cluster / image tiling cx, cy, cluster tiles per image plane
+ * ntx, nty, CTAs per plane}; zeros otherwise.  Not needed to call the operators. */
+#define CSPN_TRANSPORT_CLUSTER 0 /* hardware clusters of cx x cy CTAs, halo ring through DSMEM, decaying margins between cluster tiles */
+#define CSPN_TRANSPORT_STREAM 1  /* an image = cx x cy tiles, halo ring through global-memory inboxes, persistent cooperative grid */
+#define CSPN_TRANSPORT_HYBRID 2  /* an image = cy hardware clusters of (cx, 1): left / right through DSMEM, up / down through the inboxes */
 #define CSPN_KERNEL_GENERIC 0
 #define CSPN_KERNEL_SINGLE 1  /* one 64 x 80 register tile per CTA, hardware clusters (DSMEM) or persistent stream (cspn_fused3x3.cuh) */
 #define CSPN_KERNEL_DUAL 2    /* two register tiles per CTA worked on alternately, halo messages through L2 (cspn_dual3x3.cu) */

@@ -87,7 +87,7 @@ def test_planner_picks_kernel_and_workspace_by_problem_size():
     assert _lib.forward_plan(8, 1, 228, 304, 24)["kernel"] == _lib.KERNEL_SINGLE
     assert lib.cspn_fwd_workspace_bytes(1, 1, 228, 304, 24, 3, 0) == 0                 # one 5x3 cluster: DSMEM
     assert lib.cspn_fwd_workspace_bytes(7, 1, 228, 304, 24, 3, 0) == 0                 # 7 clusters of 15 fit at once
-    assert lib.cspn_fwd_workspace_bytes(8, 1, 228, 304, 24, 3, 0) == 256 + 8 * 15 * inbox    # the 8th would not: stream mode, status word + 120 inboxes
+    assert lib.cspn_fwd_workspace_bytes(8, 1, 228, 304, 24, 3, 0) == 256 + 8 * 15 * inbox    # the 8th would not: row clusters + global inboxes (or stream mode), status word + 120 inboxes
     assert lib.cspn_fwd_workspace_bytes(32, 1, 352, 1216, 24, 3, 0) == 0               # KITTI batch: 4x2 hardware clusters
     assert lib.cspn_fwd_workspace_bytes(8, 1, 64, 64, 24, 3, 0) == 0                   # single-tile images
     # one image with more tiles than SMs (720p: 22 x 10 = 220): never the lockstep stream (it would wait on tiles that have

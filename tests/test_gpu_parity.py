@@ -517,3 +517,16 @@ def test_pipelined_host_entry_points():
     t0 = ctypes.c_int(5)
     assert lib.cspn_fwd_host_submit_f32(hg.data_ptr(), 8, hd.data_ptr(), None, 1, out.data_ptr(), 0, 1, 4, 4, 2, 3, 0, ctypes.byref(t0)) == 0 and t0.value == 0   # empty batch
     assert lib.cspn_fwd_host_submit_f32(None, 8 * 16, hd.data_ptr(), None, 1, out.data_ptr(), 1, 1, 4, 4, 2, 3, 0, ctypes.byref(t0)) == -1
+
+
+def test_hybrid_row_cluster_transport():
+    """Row-cluster transport of the forward kernel (every tile row of an image = one hardware cluster: DSMEM left / right, global
+    inboxes up / down, row rims shipped from inside the sweep), forced with CSPN_EXCHANGE=hybrid: plan, parity vs the C oracle in
+    both modes and precisions, fall-back plans when the clusters do not fit at once, CUDA-graph replay."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CSPN_EXCHANGE="hybrid")
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "hybrid_worker.py")], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok hybrid"), r.stdout[-2000:] + r.stderr[-4000:]

@@ -42,3 +42,15 @@ print("  push step (last one): sweep %.0f, fence %.0f, issue bulk %.0f cycles (m
     np.median(d[:, :, 1] - d[:, :, 0]), np.median(d[:, :, 2] - d[:, :, 1]), np.median(d[:, :, 3] - d[:, :, 2])))
 for w in range(8):
     print("    warp %d: sweep %.0f fence %.0f bulk %.0f" % (w, np.median(d[:, w, 1] - d[:, w, 0]), np.median(d[:, w, 2] - d[:, w, 1]), np.median(d[:, w, 3] - d[:, w, 2])))
+print("  per warp: exchange_rows even/odd | refresh wait | compute even/odd (medians over CTAs and steps)")
+for w in range(8):
+    print("    warp %d: %5.0f %5.0f | %5.0f | %5.0f %5.0f" % (w, np.median(ex[:, w, 2::2]), np.median(ex[:, w, 1::2]), np.median(wait[:, w, 2::2]),
+                                                          np.median(comp[:, w, 0::2]), np.median(comp[:, w, 1::2])))
+ctas_by_row = {r: [c for c in range(nctas) if (c // 5) % 3 == r] for r in range(3)}
+for r, cs in ctas_by_row.items():
+    print("  tile row %d: refresh wait median %.0f (warp 0 %.0f, warp 7 %.0f)" % (r, np.median(wait[cs][:, :, 2::2]), np.median(wait[cs][:, 0, 2::2]), np.median(wait[cs][:, 7, 2::2])))
+print("  last refresh (t = 22), per warp, medians over CTAs: after row exchange -> polls done | -> mbarrier done | -> applied")
+for w in range(8):
+    a, b, c, d = rel[:, w, 17 + 66], rel[:, w, 93], rel[:, w, 94], rel[:, w, 18 + 66]
+    print("    warp %d: %5.0f | %5.0f | %5.0f     (row exchange itself %5.0f)" % (w, np.median(b - a), np.median(c - b), np.median(d - c), np.median(a - rel[:, w, 16 + 66])))
+print("  re-polls per warp over the whole launch (median / max over CTAs): " + "  ".join("%d/%d" % (np.median(tr[:, w, 95]), tr[:, w, 95].max()) for w in range(8)))
