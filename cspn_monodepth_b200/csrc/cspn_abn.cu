@@ -56,51 +56,86 @@ __device__ __forceinline__ void block_sum2(double& a, double& b, double* sh /* [
     }
 }
 
-// Walk the elements [m0, m1) of channel c (flat index m = n * S + s) and feed them to f(value index in memory).
-template <typename F>
-__device__ __forceinline__ void for_channel_range(long m0, long m1, int c, int C, int S, F f)
+// Walk the elements [m0, m1) of channel c (flat index m = n * S + s): piece by piece (one piece per image the range touches), with
+// four independent 16-byte loads per thread in flight when vec (S, m0, m1 multiples of 4 and 16-byte aligned planes), else scalar.
+// ld4(i) / ld1(i) load at float index i, use4 / use1 consume what they returned.
+template <typename L4, typename U4, typename L1, typename U1>
+__device__ __forceinline__ void for_channel_range(long m0, long m1, int c, int C, int S, bool vec, L4 ld4, U4 use4, L1 ld1, U1 use1)
 {
     long m = m0;
     while (m < m1) {
         const int n = (int)(m / S), s0 = (int)(m - (long)n * S);
         const int len = (int)((m1 - m) < (long)(S - s0) ? (m1 - m) : (long)(S - s0));
         const size_t base = ((size_t)n * C + c) * S + s0;
-        for (int i = threadIdx.x; i < len; i += kAT) f(base + i);
+        if (vec) {
+            int i = 4 * threadIdx.x;
+            for (; i + 12 * kAT < len; i += 16 * kAT) {
+                const auto v0 = ld4(base + i), v1 = ld4(base + i + 4 * kAT), v2 = ld4(base + i + 8 * kAT), v3 = ld4(base + i + 12 * kAT);
+                use4(v0); use4(v1); use4(v2); use4(v3);
+            }
+            for (; i < len; i += 4 * kAT) use4(ld4(base + i));
+        } else {
+            for (int i = threadIdx.x; i < len; i += kAT) use1(ld1(base + i));
+        }
         m += len;
     }
 }
 
-// stage 1 of the statistics: partial[c][slab] = {sum x, sum x^2} over the slab's elements
-__global__ void __launch_bounds__(kAT) abn_stats_kernel(const float* __restrict__ x, double* __restrict__ partial, int N, int C, int S, int slabs)
+// slab s of a channel covers [s * L, (s + 1) * L) of its N * S elements; L is a multiple of 4 so that vector pieces stay aligned
+__device__ __forceinline__ void slab_range(int N, int S, int slabs, int slab, long& m0, long& m1)
+{
+    const long M = (long)N * S;
+    const long L = (((M + slabs - 1) / slabs) + 3) & ~3l;
+    m0 = (long)slab * L < M ? (long)slab * L : M;
+    m1 = m0 + L < M ? m0 + L : M;
+}
+
+// stage 1 of the statistics: partial[c][slab] = {sum x, sum x^2} over the slab's elements (groups of four summed in fp32, groups in double)
+__global__ void __launch_bounds__(kAT) abn_stats_kernel(const float* __restrict__ x, double* __restrict__ partial, int N, int C, int S, int slabs, int vec)
 {
     __shared__ double sh[2 * (kAT / 32)];
     const int c = blockIdx.y, slab = blockIdx.x;
-    const long M = (long)N * S, L = (M + slabs - 1) / slabs;
-    const long m0 = (long)slab * L, m1 = m0 + L < M ? m0 + L : M;
+    long m0, m1;
+    slab_range(N, S, slabs, slab, m0, m1);
     double a = 0.0, b = 0.0;
-    for_channel_range(m0, m1, c, C, S, [&](size_t i) { const double v = (double)x[i]; a += v; b = fma(v, v, b); });
+    for_channel_range(m0, m1, c, C, S, vec != 0,
+        [&](size_t i) { return __ldg(reinterpret_cast<const float4*>(x + i)); },
+        [&](float4 v) { a += (double)((v.x + v.y) + (v.z + v.w)); b += (double)(fmaf(v.x, v.x, v.y * v.y) + fmaf(v.z, v.z, v.w * v.w)); },
+        [&](size_t i) { return __ldg(x + i); },
+        [&](float v) { a += (double)v; b = fma((double)v, (double)v, b); });
     block_sum2(a, b, sh);
     if (threadIdx.x == 0) { partial[((size_t)c * slabs + slab) * 2] = a; partial[((size_t)c * slabs + slab) * 2 + 1] = b; }
 }
 
 // stage 1 of the backward: partial = {sum dz', sum y dz'} with the activation undone on the fly
+struct ZD4 { float4 z, d; };
+struct ZD1 { float z, d; };
 __global__ void __launch_bounds__(kAT) abn_bwd_reduce_kernel(const float* __restrict__ z, const float* __restrict__ dz, const float* __restrict__ weight,
                                                              const float* __restrict__ bias, double* __restrict__ partial, int N, int C, int S, int slabs,
-                                                             float eps, int act, float slope)
+                                                             float eps, int act, float slope, int vec)
 {
     __shared__ double sh[2 * (kAT / 32)];
     const int c = blockIdx.y, slab = blockIdx.x;
-    const long M = (long)N * S, L = (M + slabs - 1) / slabs;
-    const long m0 = (long)slab * L, m1 = m0 + L < M ? m0 + L : M;
+    long m0, m1;
+    slab_range(N, S, slabs, slab, m0, m1);
     const float gamma = weight ? fabsf(weight[c]) + eps : 1.f, beta = bias ? bias[c] : 0.f;
+    const float inv_gamma = 1.f / gamma;               // y = (z - beta) * (1 / gamma): one rounding more than the reference's division, 30 % fewer instructions
     double a = 0.0, b = 0.0;
-    for_channel_range(m0, m1, c, C, S, [&](size_t i) {
-        float zz = z[i], d = dz[i];
+    auto one = [&](float zz, float d, float& sd, float& syd) {
         act_undo(zz, d, act, slope);
-        const float y = (zz - beta) / gamma;
-        a += (double)d;
-        b += (double)(y * d);
-    });
+        const float y = (zz - beta) * inv_gamma;
+        sd += d;
+        syd = fmaf(y, d, syd);
+    };
+    for_channel_range(m0, m1, c, C, S, vec != 0,
+        [&](size_t i) { return ZD4{__ldg(reinterpret_cast<const float4*>(z + i)), __ldg(reinterpret_cast<const float4*>(dz + i))}; },
+        [&](ZD4 v) {
+            float sd = 0.f, syd = 0.f;
+            one(v.z.x, v.d.x, sd, syd); one(v.z.y, v.d.y, sd, syd); one(v.z.z, v.d.z, sd, syd); one(v.z.w, v.d.w, sd, syd);
+            a += (double)sd; b += (double)syd;
+        },
+        [&](size_t i) { return ZD1{__ldg(z + i), __ldg(dz + i)}; },
+        [&](ZD1 v) { float sd = 0.f, syd = 0.f; one(v.z, v.d, sd, syd); a += (double)sd; b += (double)syd; });
     block_sum2(a, b, sh);
     if (threadIdx.x == 0) { partial[((size_t)c * slabs + slab) * 2] = a; partial[((size_t)c * slabs + slab) * 2 + 1] = b; }
 }
@@ -144,13 +179,20 @@ __global__ void __launch_bounds__(kAT) abn_forward_kernel(float* __restrict__ x,
     float* p = x + (size_t)plane * S;
     const int s0 = blockIdx.y * kSegElems, s1 = s0 + kSegElems < S ? s0 + kSegElems : S;
     if (vec) {
-        for (int s = s0 + 4 * threadIdx.x; s < s1; s += 4 * kAT) {
-            float4 v = *reinterpret_cast<float4*>(p + s);
-            v.x = act_forward((v.x - mu) * is * gamma + beta, act, slope);
-            v.y = act_forward((v.y - mu) * is * gamma + beta, act, slope);
-            v.z = act_forward((v.z - mu) * is * gamma + beta, act, slope);
-            v.w = act_forward((v.w - mu) * is * gamma + beta, act, slope);
-            *reinterpret_cast<float4*>(p + s) = v;
+        // a segment is 4 x 16 bytes per thread: all four loads are issued before the first store
+        constexpr int kPer = kSegElems / (4 * kAT);
+        float4 v[kPer];
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) { const int s = s0 + 4 * (threadIdx.x + k * kAT); if (s < s1) v[k] = *reinterpret_cast<const float4*>(p + s); }
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            const int s = s0 + 4 * (threadIdx.x + k * kAT);
+            if (s >= s1) continue;
+            v[k].x = act_forward((v[k].x - mu) * is * gamma + beta, act, slope);
+            v[k].y = act_forward((v[k].y - mu) * is * gamma + beta, act, slope);
+            v[k].z = act_forward((v[k].z - mu) * is * gamma + beta, act, slope);
+            v[k].w = act_forward((v[k].w - mu) * is * gamma + beta, act, slope);
+            *reinterpret_cast<float4*>(p + s) = v[k];
         }
     } else {
         for (int s = s0 + threadIdx.x; s < s1; s += kAT) p[s] = act_forward((p[s] - mu) * is * gamma + beta, act, slope);
@@ -178,15 +220,24 @@ __global__ void __launch_bounds__(kAT) abn_bwd_apply_kernel(const float* __restr
     const float* pd = dz + (size_t)plane * S;
     float* po = dx + (size_t)plane * S;
     const int s0 = blockIdx.y * kSegElems, s1 = s0 + kSegElems < S ? s0 + kSegElems : S;
+    const float inv_gamma = 1.f / gamma;
     auto one = [&](float zz, float d) {
         act_undo(zz, d, act, slope);
-        const float y = (zz - beta) / gamma;
+        const float y = (zz - beta) * inv_gamma;
         return (d - edz - y * eydz) * mul;
     };
     if (vec) {
-        for (int s = s0 + 4 * threadIdx.x; s < s1; s += 4 * kAT) {
-            const float4 a = *reinterpret_cast<const float4*>(pz + s), g = *reinterpret_cast<const float4*>(pd + s);
-            *reinterpret_cast<float4*>(po + s) = make_float4(one(a.x, g.x), one(a.y, g.y), one(a.z, g.z), one(a.w, g.w));
+        constexpr int kPer = kSegElems / (4 * kAT);
+        float4 a[kPer], g[kPer];
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            const int s = s0 + 4 * (threadIdx.x + k * kAT);
+            if (s < s1) { a[k] = *reinterpret_cast<const float4*>(pz + s); g[k] = *reinterpret_cast<const float4*>(pd + s); }
+        }
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            const int s = s0 + 4 * (threadIdx.x + k * kAT);
+            if (s < s1) *reinterpret_cast<float4*>(po + s) = make_float4(one(a[k].x, g[k].x), one(a[k].y, g[k].y), one(a[k].z, g[k].z), one(a[k].w, g[k].w));
         }
     } else {
         for (int s = s0 + threadIdx.x; s < s1; s += kAT) po[s] = one(pz[s], pd[s]);
@@ -217,7 +268,8 @@ size_t abn_workspace_bytes(int C) { return (size_t)C * kMaxSlabs * 2 * sizeof(do
 int abn_stats(const float* x, int N, int C, int S, double* sums, void* ws, cudaStream_t stream)
 {
     const int slabs = slabs_for(N, C, S);
-    abn_stats_kernel<<<dim3((unsigned)slabs, (unsigned)C), kAT, 0, stream>>>(x, (double*)ws, N, C, S, slabs);
+    const int vec = (S % 4 == 0) && ((uintptr_t)x % 16 == 0);
+    abn_stats_kernel<<<dim3((unsigned)slabs, (unsigned)C), kAT, 0, stream>>>(x, (double*)ws, N, C, S, slabs, vec);
     ABN_CHECK_LAUNCH();
     abn_sum_partials_kernel<<<(C + 127) / 128, 128, 0, stream>>>((const double*)ws, sums, C, slabs);
     ABN_CHECK_LAUNCH();
@@ -246,7 +298,8 @@ int abn_bwd_reduce(const float* z, const float* dz, const float* weight, const f
                    double* sums, void* ws, cudaStream_t stream)
 {
     const int slabs = slabs_for(N, C, S);
-    abn_bwd_reduce_kernel<<<dim3((unsigned)slabs, (unsigned)C), kAT, 0, stream>>>(z, dz, weight, bias, (double*)ws, N, C, S, slabs, eps, act, slope);
+    const int vec = (S % 4 == 0) && ((uintptr_t)z % 16 == 0) && ((uintptr_t)dz % 16 == 0);
+    abn_bwd_reduce_kernel<<<dim3((unsigned)slabs, (unsigned)C), kAT, 0, stream>>>(z, dz, weight, bias, (double*)ws, N, C, S, slabs, eps, act, slope, vec);
     ABN_CHECK_LAUNCH();
     abn_sum_partials_kernel<<<(C + 127) / 128, 128, 0, stream>>>((const double*)ws, sums, C, slabs);
     ABN_CHECK_LAUNCH();
