@@ -28,9 +28,16 @@
  *   - Device entry points take DEVICE pointers, enqueue on `stream` (a cudaStream_t passed
  *     as void*; NULL = legacy default stream), never synchronise, never allocate: scratch
  *     comes from the caller (`workspace`, size from cspn_*_workspace_bytes).  They are
- *     stateless, re-entrant, usable from several host threads on different devices (the
+ *     re-entrant, usable from several host threads on different devices (the
  *     reference's DataParallel replicas, network/libs/base/encoding.py:102-105) and
- *     capturable in CUDA graphs.  Inputs are never modified; `out` must not alias inputs.
+ *     capturable in CUDA graphs.  The only state they consult is the process-wide
+ *     diagnostic override cspn_set_path() (tests / benchmarks; leave it at CSPN_PATH_AUTO
+ *     in production) and per-device capability caches; cspn_last_*() are per host thread.
+ *     Inputs are never modified; `out` must not alias inputs.
+ *   - Numerics: fp32 arithmetic with IEEE FMAs everywhere; the softmax of mode OURS uses expf
+ *     in the 3x3 kernels and `ex2.approx.ftz` (2 ulp, inputs pre-scaled by log2 e) in the
+ *     blocked 5x5 kernels - both far inside the 1e-4 parity bound, neither bit-identical to
+ *     torch.softmax.
  *   - Host entry points (cspn_fwd_host_*) take HOST pointers (pinned or pageable), do
  *     H2D copy -> kernels -> D2H copy on `stream` with stream-ordered device allocations
  *     and return after the result is in `out` (they synchronise the stream).
