@@ -38,6 +38,40 @@ __device__ __forceinline__ float go_at(const T* go1, const T* go2, int n1, int n
     return o < n1 + n2 ? to_f32(go2[((size_t)b * n2 + (o - n1)) * HW + off]) : 0.f;
 }
 
+// Gather `count` elements into shared memory with U loads per thread in flight: addr(idx) returns the global address of element idx
+// or nullptr (element is zero), put(idx, v) stores it.  The loads of a batch are predicated, not branched around, so that they
+// issue back to back - a gather loop with a branch per element serialises on the full memory latency of every element.
+template <int U, int NT, typename T, typename AddrFn, typename PutFn>
+__device__ __forceinline__ void gather_batched(int count, AddrFn addr, PutFn put)
+{
+    for (int base = threadIdx.x; base < count; base += U * NT) {
+        float v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int idx = base + u * NT;
+            const T* q = idx < count ? addr(idx) : nullptr;
+            v[u] = q ? to_f32(__ldg(q)) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int idx = base + u * NT;
+            if (idx < count) put(idx, v[u]);
+        }
+    }
+}
+template <typename T>
+__device__ __forceinline__ const T* w_ptr(const T* w1, const T* w2, int n1, int n2, int Cin, int o, int c, int tap)
+{
+    if (o < n1) return w1 + ((size_t)o * Cin + c) * 9 + tap;
+    return o < n1 + n2 ? w2 + ((size_t)(o - n1) * Cin + c) * 9 + tap : nullptr;
+}
+template <typename T>
+__device__ __forceinline__ const T* go_ptr(const T* go1, const T* go2, int n1, int n2, int b, int o, size_t HW, size_t off)
+{
+    if (o < n1) return go1 + ((size_t)b * n1 + o) * HW + off;
+    return o < n1 + n2 ? go2 + ((size_t)b * n2 + (o - n1)) * HW + off : nullptr;
+}
+
 // ---------------------------------------------------------------------------------------------------------------- forward
 template <typename T, int NO>
 __global__ void __launch_bounds__(kHT)
@@ -182,17 +216,25 @@ heads_bwd_x_kernel(const T* __restrict__ go1, const T* __restrict__ go2, const T
     const int b = blockIdx.z / nchunk, c0 = (blockIdx.z % nchunk) * kBC;
     const int i0 = blockIdx.y * kTR, j0 = blockIdx.x * kTC;
     const size_t HW = (size_t)H * W;
-    for (int idx = tid; idx < NO * kBC * 9; idx += kHT) {                  // global order (o, c, tap): coalesced reads
-        const int o = idx / (kBC * 9), ct = idx - o * (kBC * 9), c = ct / 9, tap = ct - 9 * c;
-        wsm[(o * 9 + tap) * kBC + c] = c0 + c < Cin ? w_at(w1, w2, n1, n2, Cin, o, c0 + c, tap) : 0.f;
-    }
-    for (int idx = tid; idx < NO * kGR * 66; idx += kHT) {
-        const int col = idx % 66, r = (idx / 66) % kGR, o = idx / (66 * kGR);
-        const int Y = 2 * i0 - 1 + r, X = 2 * j0 - 1 + col;
-        float v = 0.f;
-        if (Y >= 0 && Y < H && X >= 0 && X < W) v = go_at(go1, go2, n1, n2, b, o, HW, (size_t)Y * W + X);
-        gs[(o * kGR + r) * kGP + 3 + col] = v;
-    }
+    gather_batched<8, kHT, T>(NO * kBC * 9,                                                   // global order (o, c, tap): coalesced reads
+        [&](int idx) -> const T* {
+            const int o = idx / (kBC * 9), ct = idx - o * (kBC * 9), c = ct / 9, tap = ct - 9 * c;
+            return c0 + c < Cin ? w_ptr(w1, w2, n1, n2, Cin, o, c0 + c, tap) : nullptr;
+        },
+        [&](int idx, float v) {
+            const int o = idx / (kBC * 9), ct = idx - o * (kBC * 9), c = ct / 9, tap = ct - 9 * c;
+            wsm[(o * 9 + tap) * kBC + c] = v;
+        });
+    gather_batched<12, kHT, T>(NO * kGR * 66,
+        [&](int idx) -> const T* {
+            const int col = idx % 66, r = (idx / 66) % kGR, o = idx / (66 * kGR);
+            const int Y = 2 * i0 - 1 + r, X = 2 * j0 - 1 + col;
+            return (Y >= 0 && Y < H && X >= 0 && X < W) ? go_ptr(go1, go2, n1, n2, b, o, HW, (size_t)Y * W + X) : nullptr;
+        },
+        [&](int idx, float v) {
+            const int col = idx % 66, r = (idx / 66) % kGR, o = idx / (66 * kGR);
+            gs[(o * kGR + r) * kGP + 3 + col] = v;
+        });
     __syncthreads();
     float acc[2][kBC];
 #pragma unroll
@@ -268,23 +310,21 @@ heads_bwd_w_kernel(const T* __restrict__ x, const T* __restrict__ go1, const T* 
             cell_b[tid] = bb; cell_i[tid] = rem / ws; cell_j[tid] = rem % ws;
         }
         __syncthreads();
-        for (int idx = tid; idx < NO * 9 * kKC; idx += kWT) {
-            const int k = idx % kKC, ot = idx / kKC, o = ot / 9, tap = ot - 9 * o;
-            const int bb = cell_b[k];
-            float v = 0.f;
-            if (bb >= 0) {
-                const int Y = 2 * cell_i[k] + 1 - tap / 3, X = 2 * cell_j[k] + 1 - tap % 3;  // dy = 1 - ky, dx = 1 - kx
-                if (Y >= 0 && Y < H && X >= 0 && X < W) v = go_at(go1, go2, n1, n2, bb, o, HW, (size_t)Y * W + X);
-            }
-            g9[k][ot] = v;
-        }
-        for (int idx = tid; idx < 64 * kKC; idx += kWT) {
-            const int k = idx % kKC, c = idx / kKC;
-            const int bb = cell_b[k];
-            float v = 0.f;
-            if (bb >= 0 && c_base + c < Cin) v = to_f32(x[(((size_t)bb * Cin + c_base + c) * h + cell_i[k]) * w + cell_j[k]]);
-            xs[k][c] = v;
-        }
+        gather_batched<13, kWT, T>(NO * 9 * kKC,
+            [&](int idx) -> const T* {
+                const int k = idx % kKC, ot = idx / kKC, o = ot / 9, tap = ot - 9 * o;
+                const int bb = cell_b[k];
+                const int Y = 2 * cell_i[k] + 1 - tap / 3, X = 2 * cell_j[k] + 1 - tap % 3;      // dy = 1 - ky, dx = 1 - kx
+                return (bb >= 0 && Y >= 0 && Y < H && X >= 0 && X < W) ? go_ptr(go1, go2, n1, n2, bb, o, HW, (size_t)Y * W + X) : nullptr;
+            },
+            [&](int idx, float v) { g9[idx % kKC][idx / kKC] = v; });
+        gather_batched<8, kWT, T>(64 * kKC,
+            [&](int idx) -> const T* {
+                const int k = idx % kKC, c = idx / kKC;
+                const int bb = cell_b[k];
+                return (bb >= 0 && c_base + c < Cin) ? x + (((size_t)bb * Cin + c_base + c) * h + cell_i[k]) * w + cell_j[k] : nullptr;
+            },
+            [&](int idx, float v) { xs[idx % kKC][idx / kKC] = v; });
         __syncthreads();
         if (8 * og >= NO * 9) continue;                                    // row groups past the last (o, tap) only help staging
 #pragma unroll 4
@@ -306,21 +346,39 @@ heads_bwd_w_kernel(const T* __restrict__ x, const T* __restrict__ go1, const T* 
         for (int c = 0; c < 8; ++c) part[(8 * og + a) * 64 + 8 * cg + c] = acc[a][c];
 }
 
+// One CTA per (o, tap) row: 64 channels x 4 segments of the partials; every thread adds its segment in launch order, the four
+// segment sums are added in fixed order - deterministic, and the loads of a thread are independent of each other.
+constexpr int kRedSeg = 4;
 template <typename T>
-__global__ void heads_bwd_w_reduce_kernel(const float* __restrict__ partial, int nparts, T* __restrict__ gw1, T* __restrict__ gw2, int n1, int n2,
-                                          int Cin, int c_base)
+__global__ void __launch_bounds__(64 * kRedSeg)
+heads_bwd_w_reduce_kernel(const float* __restrict__ partial, int nparts, T* __restrict__ gw1, T* __restrict__ gw2, int n1, int n2, int Cin, int c_base)
 {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;           // (ot, c)
-    if (idx >= (n1 + n2) * 9 * 64) return;
-    const int c = idx % 64, ot = idx / 64, o = ot / 9, tap = ot - 9 * o;
-    if (c_base + c >= Cin) return;
+    __shared__ float seg_sum[kRedSeg][64];
+    const int ot = blockIdx.x, c = threadIdx.x & 63, seg = threadIdx.x >> 6;
+    const int per = (nparts + kRedSeg - 1) / kRedSeg, p0 = seg * per, p1 = p0 + per < nparts ? p0 + per : nparts;
+    const float* src = partial + (size_t)ot * 64 + c;
     float s = 0.f;
-    for (int p = 0; p < nparts; ++p) s += partial[(size_t)p * kOT * 64 + ot * 64 + c];       // fixed order: deterministic
-    if (o < n1) gw1[((size_t)o * Cin + c_base + c) * 9 + tap] = from_f32<T>(s);
-    else gw2[((size_t)(o - n1) * Cin + c_base + c) * 9 + tap] = from_f32<T>(s);
+    int p = p0;
+    for (; p + 8 <= p1; p += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = src[(size_t)(p + u) * kOT * 64];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    for (; p < p1; ++p) s += src[(size_t)p * kOT * 64];
+    seg_sum[seg][c] = s;
+    __syncthreads();
+    if (seg != 0 || c_base + c >= Cin) return;
+    float tot = seg_sum[0][c];
+#pragma unroll
+    for (int g = 1; g < kRedSeg; ++g) tot += seg_sum[g][c];
+    const int o = ot / 9, tap = ot - 9 * o;
+    if (o < n1) gw1[((size_t)o * Cin + c_base + c) * 9 + tap] = from_f32<T>(tot);
+    else gw2[((size_t)(o - n1) * Cin + c_base + c) * 9 + tap] = from_f32<T>(tot);
 }
 
-constexpr int kWParts = 296;              // CTAs of the backward-W kernel (2 per SM on a B200)
+constexpr int kWParts = 444;              // CTAs of the backward-W kernel (3 per SM on a B200: 121 registers x 144 threads)
 
 template <typename T, int NO>
 int heads_forward_no(const T* x, const T* w1, const T* w2, T* out1, T* out2, int n1, int n2, int B, int Cin, int h, int w, int H, int W, cudaStream_t stream)
@@ -361,7 +419,7 @@ int heads_backward_no(const T* x, const T* w1, const T* w2, const T* go1, const 
             e = cudaGetLastError();
             if (e != cudaSuccess) return (int)e;
             ++call_stats().launches;
-            heads_bwd_w_reduce_kernel<T><<<(NO * 9 * 64 + 255) / 256, 256, 0, stream>>>(ws, parts, gw1, gw2, n1, n2, Cin, c_base);
+            heads_bwd_w_reduce_kernel<T><<<(n1 + n2) * 9, 64 * kRedSeg, 0, stream>>>(ws, parts, gw1, gw2, n1, n2, Cin, c_base);
             e = cudaGetLastError();
             if (e != cudaSuccess) return (int)e;
             ++call_stats().launches;
