@@ -225,16 +225,30 @@ heads_bwd_x_kernel(const T* __restrict__ go1, const T* __restrict__ go2, const T
             const int o = idx / (kBC * 9), ct = idx - o * (kBC * 9), c = ct / 9, tap = ct - 9 * c;
             wsm[(o * 9 + tap) * kBC + c] = v;
         });
-    gather_batched<12, kHT, T>(NO * kGR * 66,
-        [&](int idx) -> const T* {
-            const int col = idx % 66, r = (idx / 66) % kGR, o = idx / (66 * kGR);
+    {
+        // grad_out window: the (row, column) pattern of a thread's elements is the same for every output channel, so its image
+        // offsets and shared-memory slots are worked out once (9 elements of the 17 x 66 window per thread) and the loop over the
+        // outputs only adds plane bases: 9 independent loads per thread and output in flight, ~3 integer instructions per element.
+        constexpr int kWin = kGR * 66, kPerT = (kWin + kHT - 1) / kHT;
+        int goff[kPerT], soff[kPerT];
+#pragma unroll
+        for (int u = 0; u < kPerT; ++u) {
+            const int e = tid + u * kHT, r = e / 66, col = e - 66 * r;
             const int Y = 2 * i0 - 1 + r, X = 2 * j0 - 1 + col;
-            return (Y >= 0 && Y < H && X >= 0 && X < W) ? go_ptr(go1, go2, n1, n2, b, o, HW, (size_t)Y * W + X) : nullptr;
-        },
-        [&](int idx, float v) {
-            const int col = idx % 66, r = (idx / 66) % kGR, o = idx / (66 * kGR);
-            gs[(o * kGR + r) * kGP + 3 + col] = v;
-        });
+            soff[u] = e < kWin ? r * kGP + 3 + col : -1;
+            goff[u] = (e < kWin && Y >= 0 && Y < H && X >= 0 && X < W) ? Y * W + X : -1;
+        }
+#pragma unroll 1
+        for (int o = 0; o < NO; ++o) {
+            const T* plane = go_ptr(go1, go2, n1, n2, b, o, HW, 0);          // nullptr: padded output row
+            float v[kPerT];
+#pragma unroll
+            for (int u = 0; u < kPerT; ++u) v[u] = (plane && goff[u] >= 0) ? to_f32(__ldg(plane + goff[u])) : 0.f;
+#pragma unroll
+            for (int u = 0; u < kPerT; ++u)
+                if (soff[u] >= 0) gs[o * kGR * kGP + soff[u]] = v[u];
+        }
+    }
     __syncthreads();
     float acc[2][kBC];
 #pragma unroll
@@ -283,7 +297,7 @@ constexpr int kWT = kOT / 8 * 8;          // threads of the backward-W kernel: 1
 constexpr int kOTP = kOT + 4;
 
 template <typename T, int NO>
-__global__ void __launch_bounds__(kWT)
+__global__ void __launch_bounds__(kWT, 3)
 heads_bwd_w_kernel(const T* __restrict__ x, const T* __restrict__ go1, const T* __restrict__ go2, float* __restrict__ partial,
                    int n1, int n2, int Cin, int h, int w, int H, int W, int B, int c_base)
 {
@@ -310,21 +324,48 @@ heads_bwd_w_kernel(const T* __restrict__ x, const T* __restrict__ go1, const T* 
             cell_b[tid] = bb; cell_i[tid] = rem / ws; cell_j[tid] = rem % ws;
         }
         __syncthreads();
-        gather_batched<13, kWT, T>(NO * 9 * kKC,
-            [&](int idx) -> const T* {
-                const int k = idx % kKC, ot = idx / kKC, o = ot / 9, tap = ot - 9 * o;
-                const int bb = cell_b[k];
-                const int Y = 2 * cell_i[k] + 1 - tap / 3, X = 2 * cell_j[k] + 1 - tap % 3;      // dy = 1 - ky, dx = 1 - kx
-                return (bb >= 0 && Y >= 0 && Y < H && X >= 0 && X < W) ? go_ptr(go1, go2, n1, n2, bb, o, HW, (size_t)Y * W + X) : nullptr;
-            },
-            [&](int idx, float v) { g9[idx % kKC][idx / kKC] = v; });
-        gather_batched<8, kWT, T>(64 * kKC,
-            [&](int idx) -> const T* {
-                const int k = idx % kKC, c = idx / kKC;
-                const int bb = cell_b[k];
-                return (bb >= 0 && c_base + c < Cin) ? x + (((size_t)bb * Cin + c_base + c) * h + cell_i[k]) * w + cell_j[k] : nullptr;
-            },
-            [&](int idx, float v) { xs[idx % kKC][idx / kKC] = v; });
+        if (tid < 4 * kKC) {
+            // staging role of a thread: cell sk of the chunk, taps sq, sq + 4 (, sq + 8) of every output and channels sq + 4 u.  The
+            // cell's image position is worked out once; all 3 NO + 16 loads of the thread are independent and issued together.
+            const int sk = tid & (kKC - 1), sq = tid / kKC;
+            const int bb = cell_b[sk], ci = cell_i[sk], cj = cell_j[sk];
+            int toff[3];                                                                  // in-plane offset of the thread's taps, -1: not loaded
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {
+                const int tap = sq + 4 * m, ky = tap / 3, kx = tap - 3 * ky;
+                const int Y = 2 * ci + 1 - ky, X = 2 * cj + 1 - kx;                       // dy = 1 - ky, dx = 1 - kx
+                toff[m] = (bb >= 0 && tap < 9 && Y >= 0 && Y < H && X >= 0 && X < W) ? Y * W + X : -1;
+            }
+            constexpr int kOG = 4;                                                        // outputs per batch: 12 loads in flight
+#pragma unroll 1
+            for (int o0 = 0; o0 < NO; o0 += kOG) {
+                float gv[kOG][3];
+#pragma unroll
+                for (int oo = 0; oo < kOG; ++oo) {
+                    const T* plane = (o0 + oo < NO && bb >= 0) ? go_ptr(go1, go2, n1, n2, bb, o0 + oo, HW, 0) : nullptr;
+#pragma unroll
+                    for (int m = 0; m < 3; ++m) gv[oo][m] = (plane && toff[m] >= 0) ? to_f32(__ldg(plane + toff[m])) : 0.f;
+                }
+#pragma unroll
+                for (int oo = 0; oo < kOG; ++oo)
+#pragma unroll
+                    for (int m = 0; m < 3; ++m)
+                        if (o0 + oo < NO && sq + 4 * m < 9) g9[sk][(o0 + oo) * 9 + sq + 4 * m] = gv[oo][m];
+            }
+            const T* xc = bb >= 0 ? x + (((size_t)bb * Cin + c_base) * h + ci) * w + cj : nullptr;
+            const size_t cstride = (size_t)h * w;
+#pragma unroll 1
+            for (int u0 = 0; u0 < 16; u0 += 8) {
+                float xv[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int c = sq + 4 * (u0 + u);
+                    xv[u] = (xc && c_base + c < Cin) ? to_f32(__ldg(xc + c * cstride)) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) xs[sk][sq + 4 * (u0 + u)] = xv[u];
+            }
+        }
         __syncthreads();
         if (8 * og >= NO * 9) continue;                                    // row groups past the last (o, tap) only help staging
 #pragma unroll 4
@@ -435,7 +476,8 @@ size_t heads_workspace_bytes() { return (size_t)kWParts * kOT * 64 * sizeof(floa
 bool heads_supported(int n1, int n2, int Cin, int h, int w, int H, int W)
 {
     const int no = n1 + n2;
-    return n1 >= 1 && n2 >= 0 && no <= 16 && Cin >= 1 && Cin <= kMaxCin && h >= 1 && w >= 1 && H >= 1 && W >= 1 && H <= 2 * h && W <= 2 * w;
+    return n1 >= 1 && n2 >= 0 && no <= 16 && Cin >= 1 && Cin <= kMaxCin && h >= 1 && w >= 1 && H >= 1 && W >= 1 && H <= 2 * h && W <= 2 * w &&
+           (long)H * W < (1l << 31);                  // in-plane offsets are ints
 }
 
 // kernels are instantiated for the output counts of the reference's models (1 + 8 = 9, unet_ours.py:278-279; 1 + 12 = 13,
