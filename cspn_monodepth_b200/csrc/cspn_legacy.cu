@@ -85,18 +85,19 @@ legacy_kernel(const T* __restrict__ g, int64_t gbs, const TIn* __restrict__ rin,
     {
         const T* gb = g + (size_t)b * gbs;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            load_quad(gb + (size_t)k * hw, gy, gx, H, W, vec != 0, gk[k]);
-#pragma unroll
-            for (int q = 0; q < kQuad; ++q) gk[k][q] = fabsf(gk[k][q]);                       // CSPN.py:22-29
-            *reinterpret_cast<float4*>(&hp[0][k][ry + 1][qx * kQuad]) = hsum3(gk[k], qx);
-        }
+        for (int k = 0; k < 8; ++k) load_quad(gb + (size_t)k * hw, gy, gx, H, W, vec != 0, gk[k]);      // all loads first: the shuffles below would serialise them
     }
     float rq[kQuad], mq[kQuad], sq[kQuad], in[kQuad];
     load_quad(rin + (size_t)b * hw, gy, gx, H, W, vec != 0, rq);
     mq[0] = mq[1] = mq[2] = mq[3] = 0.f;
     sq[0] = sq[1] = sq[2] = sq[3] = 0.f;
     if (sparse) load_quad(sparse + (size_t)b * hw, gy, gx, H, W, vec != 0, sq);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+#pragma unroll
+        for (int q = 0; q < kQuad; ++q) gk[k][q] = fabsf(gk[k][q]);                           // CSPN.py:22-29
+        *reinterpret_cast<float4*>(&hp[0][k][ry + 1][qx * kQuad]) = hsum3(gk[k], qx);
+    }
 #pragma unroll
     for (int q = 0; q < kQuad; ++q) {
         in[q] = (gy >= 0 && gy < H && gx + q >= 0 && gx + q < W) ? 1.f : 0.f;
