@@ -207,8 +207,9 @@ struct FusedParams {
     T* gg; T* gd;         // dL/d guidance [B, Cg, H, W], dL/d depth [B, 1, H, W]
     int Cg;
     int Ctot, ch0;        // backward works on depth channel ch0 of Ctot (one launch per channel; the forward takes all planes at once)
-    float* hist;          // history scratch: hist_slots tiles of iters x TH x 64 floats, one per SM id
-    int hist_slots;
+    float* hist;          // history scratch: hist_slots tiles of iters x TH x 64 floats
+    int hist_slots;       // hist_by_cta: one per CTA of the launch (launches of at most kHistSlots CTAs, every stream-mode launch);
+    int hist_by_cta;      // otherwise one per SM id (%smid), so that the scratch stays L2-sized however many CTAs the launch has
 };
 
 // Global-memory halo inbox of one CTA (GLB exchange), in uint4 units.  Every message is one 16-byte store
@@ -806,7 +807,7 @@ __device__ __forceinline__ void fused_tile(const FusedParams<T>& p, const CUtens
     // problem is.  The reverse phase reads the tiles back with cp.async.
     float* hist_cta = nullptr;
     if (BWD) {
-        const uint32_t slot = sm_id();
+        const uint32_t slot = p.hist_by_cta ? (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x : sm_id();
         if (slot >= (uint32_t)p.hist_slots) poisoned = true;          // unknown SM numbering: fail loudly (NaN gradients)
         hist_cta = p.hist + (size_t)(slot % (uint32_t)p.hist_slots) * (size_t)p.iters * (TH * kTileW);
     }

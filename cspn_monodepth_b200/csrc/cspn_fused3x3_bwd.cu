@@ -10,7 +10,20 @@ namespace cspn {
 namespace {
 constexpr int kTHBwd = kNWBwd * kPBwd;
 inline size_t up256(size_t v) { return (v + 255) & ~(size_t)255; }
-inline size_t hist_bytes(int iters) { return (size_t)kHistSlots * (size_t)iters * kTHBwd * kTileW * sizeof(float); }
+// History scratch slots of a launch: one per CTA when the launch has at most kHistSlots CTAs (always in stream mode: the persistent
+// grid has at most one CTA per SM), else one per SM id.
+inline int hist_slots_for(const Tiling& tl, int B, const Capacity& cap)
+{
+    const long total = tl.ctas * (long)B;
+    const long ctas = tl.stream ? (total < cap.sms ? total : (long)cap.sms) : total;
+    return ctas <= kHistSlots ? (int)ctas : kHistSlots;
+}
+inline bool hist_by_cta(const Tiling& tl, int B, const Capacity& cap)
+{
+    const long total = tl.ctas * (long)B;
+    return (tl.stream ? (total < cap.sms ? total : (long)cap.sms) : total) <= kHistSlots;
+}
+inline size_t hist_bytes(int iters, int slots) { return (size_t)slots * (size_t)iters * kTHBwd * kTileW * sizeof(float); }
 // grad_guidance of one more depth channel, accumulated into the result (the affinity is shared by the channels of an image,
 // pac.py:118-119): channels 0..7 only, the rest stays zero
 template <typename T>
@@ -43,18 +56,21 @@ bool fused_bwd_supported(int C, int H, int W, int iters, int ksize, int mode)
 
 size_t fused_bwd_workspace(int B, int C, int H, int W, int iters)
 {
-    const Tiling tl = choose_tiling(H, W, iters, kTHBwd, (long)B, capacity<kPBwd, kNWBwd, true>());
+    const Capacity cap = capacity<kPBwd, kNWBwd, true>();
+    const Tiling tl = choose_tiling(H, W, iters, kTHBwd, (long)B, cap);
     if (!tl.ok) return 0;
-    return bwd_inbox_bytes(tl, B) + hist_bytes(iters) + gg_scratch_bytes(B, C, H, W);
+    return bwd_inbox_bytes(tl, B) + hist_bytes(iters, hist_slots_for(tl, B, cap)) + gg_scratch_bytes(B, C, H, W);
 }
 
 template <typename T>
 int fused_backward(const BwdArgs<T>& a)
 {
-    const Tiling tl = choose_tiling(a.H, a.W, a.iters, kTHBwd, (long)a.B, capacity<kPBwd, kNWBwd, true>());
+    const Capacity cap = capacity<kPBwd, kNWBwd, true>();
+    const Tiling tl = choose_tiling(a.H, a.W, a.iters, kTHBwd, (long)a.B, cap);
     if (!tl.ok || a.C < 1 || a.C > 16) return CSPN_ERR_BAD_KERNEL_SIZE;
     if ((long)a.B > 65535) return CSPN_ERR_BAD_SHAPE;
-    const size_t inbox = bwd_inbox_bytes(tl, a.B), hist = hist_bytes(a.iters);
+    const int slots = hist_slots_for(tl, a.B, cap);
+    const size_t inbox = bwd_inbox_bytes(tl, a.B), hist = hist_bytes(a.iters, slots);
     if (!a.ws || a.ws_bytes < inbox + hist + gg_scratch_bytes(a.B, a.C, a.H, a.W)) return CSPN_ERR_WORKSPACE;
     const size_t hw = (size_t)a.H * a.W;
     if (a.Cg > 8) {
@@ -66,7 +82,7 @@ int fused_backward(const BwdArgs<T>& a)
     p.g = a.guidance; p.gbs = a.gbs; p.depth = a.depth; p.sparse = a.sparse; p.sparse_channels = a.sparse_channels; p.out = nullptr;
     p.C = 1; p.H = a.H; p.W = a.W; p.iters = a.iters;
     p.gout = a.grad_out; p.gd = a.grad_depth; p.Ctot = a.C;
-    p.hist = (float*)((char*)a.ws + inbox); p.hist_slots = kHistSlots;
+    p.hist = (float*)((char*)a.ws + inbox); p.hist_slots = slots; p.hist_by_cta = hist_by_cta(tl, a.B, cap) ? 1 : 0;
     T* const scratch = (T*)((char*)a.ws + inbox + hist);
     // One launch per depth channel (the channels of an image share the affinity, pac.py:77-78,118-119): channel 0 writes
     // grad_guidance, every further channel writes an 8-channel scratch that is added on.

@@ -80,8 +80,8 @@ def test_workspace_queries():
 def test_planner_picks_kernel_and_workspace_by_problem_size():
     """The workspace query runs the same planner as the launch (B200 cluster capacities as defaults without a GPU):
     hardware clusters need no scratch, stream mode one 16-byte-slot inbox per tile (576 slots for a 64x80 tile) and only
-    when a whole image is resident at once, the blocked 5x5 path two fp32 planes, the fused backward the per-SM history
-    (192 slots x T x 64 x 64 floats)."""
+    when a whole image is resident at once, the blocked 5x5 path two fp32 planes, the fused backward its history scratch
+    (T x 64 x 64 floats per slot: one slot per CTA for launches of up to 192 CTAs - every stream-mode launch -, else 192 SM-id slots)."""
     lib = _lib.load()
     inbox = (4 * 80 + 4 * 2 * 32) * 16
     assert _lib.forward_plan(8, 1, 228, 304, 24)["kernel"] == _lib.KERNEL_SINGLE
@@ -99,10 +99,11 @@ def test_planner_picks_kernel_and_workspace_by_problem_size():
     assert _lib.forward_plan(1, 1, 20, 30, 4, 7, 1)["kernel"] == _lib.KERNEL_GENERIC
     assert lib.cspn_fwd_workspace_bytes(16, 1, 480, 640, 12, 5, 1) == 2 * 16 * 480 * 640 * 4
     assert lib.cspn_fwd_workspace_bytes(16, 1, 480, 640, 4, 5, 1) == 0                 # one launch: no hand-over planes
-    hist = 192 * 24 * 64 * 64 * 4
-    assert lib.cspn_bwd_workspace_bytes(1, 1, 60, 60, 24, 3, 0) == hist                # one tile: history only
+    tile_hist = 24 * 64 * 64 * 4                                                       # history of one tile: T x 64 x 64 floats
+    assert lib.cspn_bwd_workspace_bytes(1, 1, 60, 60, 24, 3, 0) == tile_hist           # one tile, one CTA: one history slot
     n = lib.cspn_bwd_workspace_bytes(8, 1, 228, 304, 24, 3, 0)
-    assert n == hist + 256 + 8 * 20 * (4 * 64 + 4 * 2 * 32) * 16                       # stream mode: status word + 20 tiles of 64x64 per image
+    # stream mode: status word + 20 tiles of 64x64 per image, history slots = the persistent grid (148 CTAs for 160 tiles)
+    assert n == 148 * tile_hist + 256 + 8 * 20 * (4 * 64 + 4 * 2 * 32) * 16
 
 
 def test_dual_slot_planner_is_opt_in():
