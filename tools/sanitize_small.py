@@ -28,3 +28,24 @@ g, d, s = make_inputs(3, 1, 24, 1, 40, 70, density=0.05)
 y = cspn_ours.AffinityPropagate(6)(cu(d), cu(g), sparse_depth=cu(s))
 torch.cuda.synchronize()
 print("5x5 err %.2e" % np.abs(y.cpu().numpy() - c_oracle.forward(g, d, s, 6, 5, 1)).max(), flush=True)
+
+# the neighbours of the module: heads forward + backward, masked L1 + metrics, in-place ABN forward + backward, legacy CSPN
+from cspn_monodepth_b200 import abn, criteria, cspn_legacy, heads
+rng = np.random.default_rng(9)
+x = cu(rng.standard_normal((2, 20, 19, 27)).astype(np.float32)).requires_grad_(True)
+wd = cu((rng.standard_normal((1, 20, 3, 3)) / 8).astype(np.float32)).requires_grad_(True)
+wg = cu((rng.standard_normal((12, 20, 3, 3)) / 8).astype(np.float32)).requires_grad_(True)
+dd, gg_ = heads.guidance_depth_heads(x, wd, wg, 37, 53)
+sp = cu(((rng.random((2, 1, 37, 53)) < 0.1) * 3.0).astype(np.float32))
+tgt = cu((rng.random((2, 1, 37, 53)) * 9 + 0.5).astype(np.float32))
+out = cspn_new.AffinityPropagate(4, 3)(gg_, dd, sp)
+loss = criteria.MaskedL1Loss()(out, tgt)
+loss.backward()
+res = criteria.Result(); res.evaluate(out.detach().abs() + 0.1, tgt)
+m = abn.InPlaceABN(20).to(dev)
+z = m(x * 1.0)
+z.backward(torch.ones_like(z))
+with torch.no_grad():
+    leg = cspn_legacy.legacy_propagate(gg_[:, :8].contiguous(), dd, sp, 5)
+torch.cuda.synchronize()
+print("neighbours: loss %.4f rmse %.4f abn mean %.3e legacy mean %.3f gx %.3e" % (float(loss.detach()), res.rmse, float(z.mean()), float(leg.mean()), float(x.grad.abs().mean())), flush=True)
