@@ -1305,9 +1305,9 @@ inline Tiling choose_tiling(int H, int W, int iters, int th, long planes, const 
             if (exchange_override() == 2) cost = 0.0;
             consider(t, cost);
         }
-        // hybrid (opt-in, CSPN_EXCHANGE=hybrid): one round by construction.  Measured 27.6-28.1 vs 28.3 us on the headline and 30.0 vs
-        // 32.3 us in mode OURS: not enough to make a transport the default that needs every cluster resident at once
-        // without a hardware guarantee for it
+        // hybrid (opt-in, CSPN_EXCHANGE=hybrid): one round by construction.  Measured 27.6-28.1 vs 28.3 us on the headline (inside the
+        // build-to-build spread), 25.9 vs 25.7 us in fp16 and 30.0 vs 32.3 us in mode OURS: not enough to replace the
+        // default transport of the headline
         if (allow_hyb && exchange_override() == 3 && t.cx >= 2 && t.cx <= 16 && t.cy >= 2 && planes <= 65535 &&
             t.cy * planes <= (long)cap.clusters[t.cx] && total <= kMaxGlobalExchangeCtas) {
             Tiling h = t; h.stream = false; h.hyb = true;
@@ -1396,21 +1396,16 @@ int launch_variant(const FusedParams<T>& p, const CUtensorMap& map, const Tiling
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = (unsigned)tl.cx; at[0].val.clusterDim.y = HYB ? 1u : (unsigned)tl.cy; at[0].val.clusterDim.z = 1;
         if (HYB) {
-            // the clusters of an image spin on each other through global memory: ask for a co-resident (cooperative) grid as
-            // well; the planner only offers this transport when the occupancy query says every cluster fits at once
+            // the clusters of an image spin on each other through global memory: the launch is cooperative as well.  Measured
+            // (tools/microbench/coopcluster.cu, driver 580 / CUDA 12.9): cluster + cooperative launches are accepted and are
+            // refused with cudaErrorCooperativeLaunchTooLarge one cluster above cudaOccupancyMaxActiveClusters - the same
+            // residency guarantee the stream transport has
             at[1].id = cudaLaunchAttributeCooperative;
             at[1].val.cooperative = 1;
             cfg.numAttrs = 2;
         }
     }
     e = cudaLaunchKernelEx(&cfg, kern, p, map);
-    if (HYB && e != cudaSuccess) {
-        // cluster + cooperative refused by this driver: plain cluster launch (co-residency rests on the occupancy query; a
-        // neighbour that never shows up ends in the bounded spin and CSPN_ERR_EXCHANGE_TIMEOUT, not in a hang)
-        cudaGetLastError();
-        cfg.numAttrs = 1;
-        e = cudaLaunchKernelEx(&cfg, kern, p, map);
-    }
     if (e != cudaSuccess) return (int)e;
     ++call_stats().launches;
     return 0;
