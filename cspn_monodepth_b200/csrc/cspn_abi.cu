@@ -419,7 +419,7 @@ size_t cspn_fwd_workspace_bytes(int B, int C, int H, int W, int iters, int ksize
         // a dual-slot-only problem may still fall through to the generic path at launch time (unaligned guidance pointer)
         const size_t f = fused_workspace(B, C, H, W, iters, ksize, mode);
         const size_t g = generic_fwd_workspace(B, C, H, W, tt.n);
-        return fused_single_possible(B, C, H, W, iters) ? f : (f > g ? f : g);
+        return fused_single_possible(B, C, H, W, iters, mode) ? f : (f > g ? f : g);
     }
     if (use_blocked(B, C, H, W, iters, ksize, mode)) return blocked5x5_workspace(B, C, H, W, iters);
     return generic_fwd_workspace(B, C, H, W, tt.n);
@@ -434,7 +434,7 @@ int cspn_fwd_plan(int B, int C, int H, int W, int iters, int ksize, int mode, in
     if (B < 1 || C < 1 || H < 1 || W < 1 || iters < 1) return CSPN_ERR_BAD_SHAPE;
     if (use_fused(B, C, H, W, iters, ksize, mode, nullptr)) {
         if (dual_supported(B, C, H, W, iters, ksize, mode)) { plan10[0] = CSPN_KERNEL_DUAL; dual_describe(B, C, H, W, iters, plan10 + 1); }
-        else { plan10[0] = CSPN_KERNEL_SINGLE; single_describe(B, C, H, W, iters, plan10 + 1); }
+        else { plan10[0] = CSPN_KERNEL_SINGLE; single_describe(B, C, H, W, iters, mode, plan10 + 1); }
     } else if (use_blocked(B, C, H, W, iters, ksize, mode)) plan10[0] = CSPN_KERNEL_BLOCKED;
     else plan10[0] = CSPN_KERNEL_GENERIC;
     return CSPN_OK;

@@ -90,7 +90,7 @@ struct Tiling { int cx, cy, ntx, nty, stepx, stepy, ew, eh; long ctas; bool ok; 
 struct Capacity { int sms; int clusters[17]; };
 bool fused_supported(int B, int C, int H, int W, int iters, int ksize, int mode);
 template <typename T> int fused_forward(const FwdArgs<T>& a);   // kDualFallback: no fused kernel takes the problem, use another path
-bool fused_single_possible(int B, int C, int H, int W, int iters);   // the single-tile kernel has a plan (any alignment)
+bool fused_single_possible(int B, int C, int H, int W, int iters, int mode);   // the single-tile kernel has a plan (any alignment)
 size_t fused_workspace(int B, int C, int H, int W, int iters, int ksize, int mode);   // optional scratch (0 = none)
 
 // dual-slot streamed forward (cspn_dual3x3.cu): two register tiles per CTA worked on alternately so that the halo
@@ -99,7 +99,7 @@ constexpr int kDualFallback = -1000;   // internal: "not this kernel" (unaligned
 bool dual_supported(int B, int C, int H, int W, int iters, int ksize, int mode);
 size_t dual_workspace(int B, int C, int H, int W, int iters);
 void dual_describe(int B, int C, int H, int W, int iters, int* out9);
-void single_describe(int B, int C, int H, int W, int iters, int* out9);   // {transport, cx, cy, ntx, nty, CTAs per plane, 0, 0, 0}
+void single_describe(int B, int C, int H, int W, int iters, int mode, int* out9);   // {transport, cx, cy, ntx, nty, CTAs per plane, 0, 0, 0}
 template <typename T> int dual_forward(const FwdArgs<T>& a);
 
 // temporally blocked forward for the 5x5 variant (cspn_blocked5x5.cu): 4 steps per launch, weights in registers

@@ -1255,7 +1255,7 @@ inline int exchange_override()
 //  * hybrid (tl.hyb, forward only): the stream tiling, but every tile ROW of an image is a hardware cluster of (cx, 1) CTAs:
 //    left / right rims through DSMEM, the rows above / below through the global inboxes, shipped from inside the sweep.  One CTA
 //    per tile, every cluster resident at once (cy * planes <= co-resident clusters of cx CTAs).
-inline Tiling choose_tiling(int H, int W, int iters, int th, long planes, const Capacity& cap, bool allow_hyb = false)
+inline Tiling choose_tiling(int H, int W, int iters, int th, long planes, const Capacity& cap, int hyb_policy = 0)
 {
     const int step_y = th - 2 * kHaloY;
     Tiling best{}; best.ok = false; best.ctas = 0; best.stream = false;
@@ -1305,13 +1305,14 @@ inline Tiling choose_tiling(int H, int W, int iters, int th, long planes, const 
             if (exchange_override() == 2) cost = 0.0;
             consider(t, cost);
         }
-        // hybrid (opt-in, CSPN_EXCHANGE=hybrid): one round by construction.  Measured 27.6-28.1 vs 28.3 us on the headline (inside the
-        // build-to-build spread), 25.9 vs 25.7 us in fp16 and 30.0 vs 32.3 us in mode OURS: not enough to replace the
-        // default transport of the headline
-        if (allow_hyb && exchange_override() == 3 && t.cx >= 2 && t.cx <= 16 && t.cy >= 2 && planes <= 65535 &&
-            t.cy * planes <= (long)cap.clusters[t.cx] && total <= kMaxGlobalExchangeCtas) {
+        // hybrid: one round by construction.  hyb_policy 0: never (backward), 1: only when forced (CSPN_EXCHANGE=hybrid), 2: by cost.
+        // Measured 27.6-28.1 vs 28.3 us on the headline (mode NEW; inside the build-to-build spread, fp16 25.9 vs
+        // 25.7 us: stays with the stream transport) and 30.0 vs 32.3 us in mode OURS (takes the hybrid transport where it fits).
+        const bool hyb_forced = exchange_override() == 3;
+        if (hyb_policy > 0 && (hyb_forced || (hyb_policy == 2 && exchange_override() == 0)) && t.cx >= 2 && t.cx <= 16 && t.cy >= 2 &&
+            planes <= 65535 && t.cy * planes <= (long)cap.clusters[t.cx] && total <= kMaxGlobalExchangeCtas) {
             Tiling h = t; h.stream = false; h.hyb = true;
-            consider(h, 0.0);
+            consider(h, hyb_forced ? 0.0 : 0.93);
         }
     }
     return best;

@@ -85,6 +85,14 @@ def test_planner_picks_kernel_and_workspace_by_problem_size():
     lib = _lib.load()
     inbox = (4 * 80 + 4 * 2 * 32) * 16
     assert _lib.forward_plan(8, 1, 228, 304, 24)["kernel"] == _lib.KERNEL_SINGLE
+    # halo transport of the single-tile kernel: 7 images fit as 5x3 hardware clusters; 8 do not - mode NEW streams, mode OURS takes
+    # the row-cluster (hybrid) transport (24 clusters of 5 <= 26 co-resident), 9 images (27 clusters) stream again
+    assert _lib.forward_plan(7, 1, 228, 304, 24)["transport"] == "cluster"
+    assert _lib.forward_plan(8, 1, 228, 304, 24, 3, 0)["transport"] == "stream"
+    p = _lib.forward_plan(8, 1, 228, 304, 24, 3, 1)
+    assert (p["transport"], p["cx"], p["cy"]) == ("hybrid", 5, 3), p
+    assert _lib.forward_plan(9, 1, 228, 304, 24, 3, 1)["transport"] == "stream"
+    assert lib.cspn_fwd_workspace_bytes(8, 1, 228, 304, 24, 3, 1) == lib.cspn_fwd_workspace_bytes(8, 1, 228, 304, 24, 3, 0)
     assert lib.cspn_fwd_workspace_bytes(1, 1, 228, 304, 24, 3, 0) == 0                 # one 5x3 cluster: DSMEM
     assert lib.cspn_fwd_workspace_bytes(7, 1, 228, 304, 24, 3, 0) == 0                 # 7 clusters of 15 fit at once
     assert lib.cspn_fwd_workspace_bytes(8, 1, 228, 304, 24, 3, 0) == 256 + 8 * 15 * inbox    # the 8th would not: row clusters + global inboxes (or stream mode), status word + 120 inboxes
