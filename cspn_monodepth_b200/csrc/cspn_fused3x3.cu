@@ -17,7 +17,11 @@ constexpr int kTHBig = kNW * kPFwd;
 
 Tiling plan_forward(int B, int C, int H, int W, int iters, int mode)
 {
-    return choose_tiling(H, W, iters, kTHBig, (long)B * C, capacity<kPFwd, kNW, false>(), mode == CSPN_MODE_OURS ? 2 : 1);
+    // hybrid transport: by cost for mode OURS only when CSPN_HYBRID_AUTO=1 (measured 7 % faster there), otherwise opt-in through
+    // CSPN_EXCHANGE=hybrid.  Not on by default: Nsight Compute cannot replay cooperative + cluster launches (LaunchFailed / illegal
+    // instruction under ncu 2025.2, fine under compute-sanitizer and in normal runs) - a default path must stay profilable.
+    static const bool hyb_auto = [] { const char* v = getenv("CSPN_HYBRID_AUTO"); return v && v[0] == '1'; }();
+    return choose_tiling(H, W, iters, kTHBig, (long)B * C, capacity<kPFwd, kNW, false>(), (hyb_auto && mode == CSPN_MODE_OURS) ? 2 : 1);
 }
 }  // namespace
 

@@ -42,6 +42,7 @@ def run(mode, shape, iters, seed, dtype=np.float32, expect_hybrid=True):
     return y
 
 
+# (CSPN_HYBRID_AUTO=1 makes the planner take this transport by cost for mode OURS; here it is forced for both modes)
 run(0, (8, 228, 304), 24, 1)                               # the headline: 24 clusters of 5
 run(0, (8, 228, 304), 24, 2, np.float16)
 run(1, (3, 228, 304), 24, 3)                               # softmax mode

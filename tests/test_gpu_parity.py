@@ -530,24 +530,3 @@ def test_hybrid_row_cluster_transport():
     env = dict(os.environ, CSPN_EXCHANGE="hybrid")
     r = subprocess.run([sys.executable, os.path.join(root, "tests", "hybrid_worker.py")], env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok hybrid"), r.stdout[-2000:] + r.stderr[-4000:]
-
-
-def test_mode_ours_takes_the_hybrid_transport_by_default():
-    """3x3 mode OURS at the headline batch: the planner picks the row-cluster transport on its own (measured 7 % faster than the
-    stream transport there); forward against the C oracle, and the backward (stream transport) still composes with it."""
-    import os
-    if os.environ.get("CSPN_EXCHANGE"):
-        pytest.skip("transport forced by the environment")
-    b, h, w = 8, 228, 304
-    assert _lib.forward_plan(b, 1, h, w, 24, 3, 1)["transport"] == "hybrid"
-    g, d, s = make_inputs(77, b, 8, 1, h, w, density=0.01)
-    tg, td, ts = (torch.from_numpy(a).cuda() for a in (g, d, s))
-    tg.requires_grad_(True); td.requires_grad_(True)
-    y = cspn_ours.AffinityPropagate(24)(td, tg, sparse_depth=ts)
-    ref = c_oracle.forward(g, d, s, 24, 3, 1, threads=0)
-    assert np.abs(y.detach().cpu().numpy() - ref).max() <= 1e-4
-    go = np.random.default_rng(3).standard_normal(d.shape).astype(np.float32)
-    y.backward(torch.from_numpy(go).cuda())
-    gg, gd = c_oracle.backward(g, d, s, go, 24, 3, 1, threads=0)
-    assert np.abs(td.grad.cpu().numpy() - gd).max() <= 1e-4 * max(1.0, np.abs(gd).max())
-    assert np.abs(tg.grad.cpu().numpy() - gg).max() <= 1e-4 * max(1.0, np.abs(gg).max())
