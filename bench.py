@@ -703,8 +703,10 @@ def unet_train_step(dev, rank, world, dist):
         return {"unavailable": "baseline/_ref is not staged"}
     if ref not in sys.path:
         sys.path.insert(0, ref)
-    from network import unet_cspn_nyu
     from cspn_monodepth_b200 import criteria, dropin
+    if torch.cuda.device_count() > 1:
+        dropin.install_inplace_abn()       # unet_cspn_nyu.py:19-25 imports InPlaceABNSync on multi-GPU boxes; the reference's needs a torch-0.4 cffi build
+    from network import unet_cspn_nyu
     torch.manual_seed(11)
     model = unet_cspn_nyu.resnet50(pretrained=False).to(dev).train()
     dropin.patch_model(model, heads=True)

@@ -139,6 +139,15 @@ def inplace_abn_sync(x, weight, bias, running_mean, running_var, extra=None, tra
     return _InPlaceABN.apply(x, weight, bias, running_mean, running_var, training, momentum, eps, activation, slope, group)
 
 
+class ABN(nn.Sequential):
+    """``bn.py:23-44``: plain ``nn.BatchNorm2d`` + activation module (no custom kernel; exported because the reference's package does)."""
+
+    def __init__(self, num_features, activation=None, **kwargs):
+        from collections import OrderedDict
+        super().__init__(OrderedDict([("bn", nn.BatchNorm2d(num_features, **kwargs)),
+                                      ("act", activation if activation is not None else nn.ReLU(inplace=True))]))
+
+
 class InPlaceABN(nn.Module):
     """``bn.py:47-110``."""
 

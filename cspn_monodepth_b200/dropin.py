@@ -5,6 +5,8 @@
   ``from network.libs.post_process.CSPN_new import AffinityPropagate`` (``unet_cspn_nyu.py:9``) and
   ``from network.libs.post_process.CSPN_ours import AffinityPropagate`` (``unet_ours.py:16``) pick them up.
   Call it before importing the UNet files.
+* :func:`install_inplace_abn` registers :mod:`cspn_monodepth_b200.abn` as ``network.libs.inplace_abn`` (needed on multi-GPU boxes,
+  where the UNet files import ``InPlaceABNSync``); :func:`install` does it as well.
 * :func:`patch_model` (``heads=True``: also the two output heads upstream, see :mod:`cspn_monodepth_b200.heads`) swaps ``model.post_process_layer`` on an already-built reference model
   (``unet_cspn_nyu.py:357-358`` / ``unet_ours.py:304-305``).  The module has no parameters or buffers,
   so checkpoints are unaffected.
@@ -14,12 +16,25 @@ import sys
 from . import cspn_new, cspn_ours
 
 
-def install():
+def install(inplace_abn=True):
     sys.modules["network.libs.post_process.CSPN_new"] = cspn_new
     sys.modules["network.libs.post_process.CSPN_ours"] = cspn_ours
     pkg = sys.modules.get("network.libs.post_process")
     if pkg is not None:
         pkg.CSPN_new, pkg.CSPN_ours = cspn_new, cspn_ours
+    if inplace_abn:
+        install_inplace_abn()
+
+
+def install_inplace_abn():
+    """Register :mod:`cspn_monodepth_b200.abn` as ``network.libs.inplace_abn``: on a box with more than one GPU both UNet files do
+    ``from network.libs.inplace_abn import InPlaceABNSync`` at import time (``unet_cspn_nyu.py:19-25``, ``unet_ours.py:23-28``), and
+    the reference's own package needs a cffi extension built against torch 0.4.  Call it before importing the UNet files."""
+    from . import abn
+    sys.modules["network.libs.inplace_abn"] = abn
+    pkg = sys.modules.get("network.libs")
+    if pkg is not None:
+        pkg.inplace_abn = abn
 
 
 def patch_model(model, heads=False):
