@@ -713,7 +713,7 @@ def unet_train_step(dev, rank, world, dist):
     ddp = model
     if dist is not None:
         from torch.nn.parallel import DistributedDataParallel
-        ddp = DistributedDataParallel(model, device_ids=[dev.index])
+        ddp = DistributedDataParallel(model, device_ids=[dev.index], find_unused_parameters=True)      # the reference model carries layers its forward never calls
     opt = torch.optim.SGD(ddp.parameters(), lr=1e-3, momentum=0.9)
     crit = criteria.MaskedL1Loss()
     gen = torch.Generator().manual_seed(100 + rank)
