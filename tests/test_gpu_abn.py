@@ -138,3 +138,15 @@ def test_sync_variant_two_replicas():
     ret = mgr.dict()
     mp.spawn(_sync_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
     assert ret.get(0) and ret.get(1)
+
+
+def test_sync_variant_over_nccl():
+    """The same check with one process per GPU and NCCL (needs two GPUs; the two-replica gloo test above covers single-GPU boxes)."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(_free_port()), os.path.join(root, "tests", "abn_nccl_worker.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ok abn nccl 2" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
