@@ -109,8 +109,7 @@ class _InPlaceABN(autograd.Function):
         with torch.cuda.device(dz.device):
             ws = torch.empty(lib.cspn_abn_workspace_bytes(c_), dtype=torch.uint8, device=dz.device)
             sums = torch.empty(2 * c_, dtype=torch.float64, device=dz.device)
-            # the parameter gradients need {sum dz, sum y dz} in eval mode too (the reference zeroes them there, functions.py:147-150,
-            # which also zeroes dweight / dbias; kept)
+            # eval mode: the reference uses edz = eydz = 0 (functions.py:147-150), which also leaves dweight / dbias at zero - kept
             if ctx.training:
                 _lib.check(lib.cspn_abn_bwd_reduce_f32(z.data_ptr(), dz.data_ptr(), _ptr(weight), _ptr(bias), n_, c_, s_, float(ctx.eps), ctx.act,
                                                        float(ctx.slope), sums.data_ptr(), ws.data_ptr(), ws.numel(), stream))
