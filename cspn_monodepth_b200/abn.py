@@ -11,8 +11,9 @@ Same names, constructor arguments, parameters / buffers (``weight``, ``bias``, `
 * ``InPlaceABNSync``: statistics over all replicas.  The reference exchanges per-GPU (mean, var) and (edz, eydz) through
   master / worker queues between ``nn.DataParallel`` threads (``functions.py:185-208``, ``:257-276``); here replicas are one
   process per GPU and the exchange is ONE all-reduce (SUM) of the [2C] double vector of per-channel sums in each direction
-  (``torch.distributed``, NCCL).  Without an initialised process group it degenerates to ``InPlaceABN``, like the reference on
-  one device.  ``devices`` is accepted and ignored.
+  (``torch.distributed``, NCCL).  Like the reference's mean of per-replica means (``functions.py:196-197``) this assumes that every
+  replica holds the same number of samples (count = local count x world size).  Without an initialised process group it
+  degenerates to ``InPlaceABN``, like the reference on one device.  ``devices`` is accepted and ignored.
 
 fp32, CUDA only, contiguous input (the reference raises ``ValueError("Non-contiguous input")``, ``functions.py:65-67``).
 Kernels: ``csrc/cspn_abn.cu`` behind ``cspn_abn_*`` (``include/cspn_b200.h``).
